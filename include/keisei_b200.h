@@ -1,0 +1,151 @@
+/*
+ * keisei_b200.h -- C ABI of the B200-native Keisei self-play rollout hot path.
+ *
+ * The reference (tachyon-beep/shogidrl) is pure Python and has no FFI of its own; the
+ * boundary it offers is duck typing (StepManager(config, game, agent, policy_mapper,
+ * experience_buffer), keisei/training/step_manager.py:61-68).  Each entry point below
+ * replaces the Python computation cited beside it (paths relative to the reference
+ * checkout).  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions: every function returns 0 on success or a negative KZ_E_* code, never
+ * throws; every data pointer is a DEVICE pointer into caller-owned memory unless marked
+ * HOST; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  No
+ * call synchronises the device.  There is no CPU fallback.
+ *
+ * Piece code: 0 empty, else 1 + type + 14*colour (type: P0 L1 N2 S3 G4 B5 R6 K7 +P8 +L9
+ * +N10 +S11 +B12 +R13; colour BLACK=0/WHITE=1 -- shogi_core_definitions.py:50-83).
+ * Square = row*9 + col.  Action index = PolicyOutputMapper's enumeration
+ * (keisei/utils/utils.py:208-266): board move ((from*80 + to - (to>from))*2 + promote),
+ * drop 12960 + to*7 + piece_type; 13,527 actions.
+ */
+#ifndef KEISEI_B200_H
+#define KEISEI_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KZ_ABI_VERSION 1
+#define KZ_NUM_ACTIONS 13527
+#define KZ_OBS_FLOATS 3726  /* 46 x 9 x 9 */
+#define KZ_MASK_PAD_STRIDE 13536 /* 16-byte multiple >= 13527: fast-path row stride */
+
+/* termination reason codes (shogi_core_definitions.py:135-147) */
+#define KZ_ONGOING 0
+#define KZ_TSUMI 1      /* "Tsumi"             */
+#define KZ_STALEMATE 2  /* "stalemate"         */
+#define KZ_MAX_MOVES 3  /* "Max moves reached" */
+#define KZ_SENNICHITE 4 /* "Sennichite"        */
+
+/* error codes */
+#define KZ_OK 0
+#define KZ_E_ARG (-1)       /* null / misaligned / out-of-range argument */
+#define KZ_E_CUDA (-2)      /* a CUDA runtime call failed (see kz_last_cuda_error) */
+#define KZ_E_NOT_INIT (-3)  /* kz_init_tables has not run on this device */
+
+/* per-env error bits (kz_errors): mirror the ValueError cases StepManager turns into a reset
+ * (step_manager.py:303-348; shogi_game.py:461-483, 529-544) */
+#define KZ_ERR_BAD_ACTION 1    /* index out of range / no own piece on source / drop not in hand or on occupied square */
+#define KZ_ERR_BAD_PATTERN 2   /* "Illegal movement pattern" */
+#define KZ_ERR_KING_CAPTURE 4  /* a king was captured (out of contract, shogi_move_execution.py:109-114) */
+#define KZ_ERR_HISTORY_FULL 8  /* more plies than hist_cap since the last reset */
+
+int kz_abi_version(void);
+const char* kz_last_cuda_error(void);
+
+/* Move/ray lookup tables -> device memory of the current device.  Idempotent. */
+int kz_init_tables(void* stream);
+
+/* Device game state is one caller-allocated blob (torch.empty(total, dtype=uint8)), SoA by
+ * field group: boards [n][96] u8, meta [n][32] u8, history [n][2][ceil(hist_cap/2)] 16-byte
+ * Zobrist-style keys (replaces the tuple history of shogi_game.py:347-372).
+ * offsets3 (HOST) receives the byte offsets of the three sections. */
+int kz_state_layout(int n, int hist_cap, int64_t* offsets3, int64_t* total_bytes);
+
+/* ShogiGame.reset (shogi_game.py:79-130) for the envs whose env_mask byte is non-zero (all
+ * if env_mask is NULL).  max_moves = ShogiGame(max_moves_per_game). */
+int kz_reset(void* state, int n, int hist_cap, const uint8_t* env_mask, int max_moves, void* stream);
+
+/* ShogiGame.from_sfen after parsing (shogi_game.py:306-329; SFEN text stays host-side):
+ * boards [n][81] piece codes, hands [n][14] (black P..R, white P..R), side [n], move_count [n],
+ * max_moves [n].  History is emptied.  Termination of the loaded position (shogi_game.py:343)
+ * is evaluated by the next kz_refresh(eval_termination=1). */
+int kz_load_positions(void* state, int n, int hist_cap, const int8_t* boards, const uint8_t* hands,
+                      const uint8_t* side, const int32_t* move_count, const int32_t* max_moves, void* stream);
+
+/* Inverse of kz_load_positions, for the scalar facade and parity dumps.
+ * meta8 [n][8] int32 = side, move_count, max_moves, status(reason), winner(-1 none), error bits,
+ * plies since reset, finished-episode counter. */
+int kz_export_positions(const void* state, int n, int hist_cap, int8_t* boards, uint8_t* hands,
+                        int32_t* meta8, void* stream);
+
+/* Outputs for the CURRENT positions without moving (all output pointers optional):
+ *   obs   generate_neural_network_observation (shogi_game_io.py:434-539), fp32, row stride
+ *         obs_stride floats (even, base 16-byte aligned);
+ *   mask  generate_all_legal_moves + PolicyOutputMapper.get_legal_mask
+ *         (shogi_rules_logic.py:486-635, utils.py:310-336), one byte per action, row stride
+ *         mask_stride bytes (>= 13527; a multiple of 16 with a 16-byte aligned base takes the
+ *         vectorised path and may zero the pad bytes);
+ *   legal_count int32 per env;
+ *   next_actions: uniform-random legal action for each env (k-th legal index in ascending
+ *         order, k = mulhi(rand32(seed, env_offset+env, rng_step), count)); int64 if
+ *         actions_i64 else int32; -1 when there is no legal move.
+ * eval_termination != 0 applies _check_and_update_termination_status to loaded positions
+ * (shogi_game.py:343, 408-450: mover := opponent of the side to move). */
+int kz_refresh(void* state, int n, int hist_cap, float* obs, int64_t obs_stride, uint8_t* mask,
+               int64_t mask_stride, int32_t* legal_count, void* next_actions, int actions_i64,
+               uint64_t seed, uint32_t rng_step, uint32_t env_offset, int eval_termination, void* stream);
+
+/* One environment step for n games: ShogiGame.make_move (shogi_game.py:574-660) fused with the
+ * legal-move generation, termination test, mask and observation of the successor, plus what
+ * StepManager does around it on `done` (reset, step_manager.py:437-440) when auto_reset != 0.
+ *   actions      [n] int64 (actions_i64) or int32 policy indices drawn from the previous mask
+ *   reward       +1 mover won / -1 mover lost / 0 (shogi_game.py:553-572), fp32
+ *   done/reason/winner  u8 / u8 (KZ_*) / i8 (0 black, 1 white, -1 none)
+ *   ep_len       move_count at termination (int32), 0 while running
+ *   obs/mask/legal_count/next_actions: as kz_refresh, for the RETURNED state (after reset when
+ *                auto_reset and done); obs of the terminal state is not materialised then.
+ * An action that fails the reference's make_move validation sets the env's error bits, leaves
+ * the game untouched and reports reward 0 / done 0. */
+int kz_step(void* state, int n, int hist_cap, const void* actions, int actions_i64, float* obs,
+            int64_t obs_stride, uint8_t* mask, int64_t mask_stride, float* reward, uint8_t* done,
+            uint8_t* reason, int8_t* winner, int32_t* ep_len, int32_t* legal_count, void* next_actions,
+            uint64_t seed, uint32_t rng_step, uint32_t env_offset, int auto_reset, void* stream);
+
+/* Thin conveniences over kz_refresh. */
+int kz_legal_mask(void* state, int n, int hist_cap, uint8_t* mask, int64_t mask_stride,
+                  int32_t* legal_count, void* stream);
+int kz_observe(void* state, int n, int hist_cap, float* obs, int64_t obs_stride, void* stream);
+
+/* Per-env error bits (KZ_ERR_*) -> out[n] int32; clear != 0 resets them. */
+int kz_errors(void* state, int n, int hist_cap, int32_t* out, int clear, void* stream);
+
+/* BaseActorCriticModel.get_action_and_value after forward() (base_actor_critic.py:64-116):
+ * masked softmax over 13,527 logits, Categorical sample (or argmax if deterministic) and
+ * log_prob with torch.distributions' probs->logits clamp (eps = FLT_EPSILON).
+ *   logits [n][ld] fp32 (logits_bf16 == 0) or bf16; mask [n][ldm] bytes; actions int64/int32;
+ *   logp fp32; entropy optional fp32.  Rows whose mask is all zero fall back to the uniform
+ *   distribution over all actions (base_actor_critic.py:93-101).  Sampling is inverse-CDF on a
+ *   counter-based uniform keyed (seed, offset + row): statistical, not bitwise, parity with
+ *   torch.multinomial. */
+int kz_sample_masked(const void* logits, int logits_bf16, int64_t ld, const uint8_t* mask, int64_t ldm,
+                     int n, uint64_t seed, uint64_t offset, void* actions, int actions_i64, float* logp,
+                     float* entropy, int deterministic, void* stream);
+
+/* ExperienceBuffer.compute_advantages_and_returns (experience_buffer.py:99-145) over a [T][N]
+ * layout, one reverse scan per env column (N = 1 is the reference's flat buffer):
+ *   delta = (r + (gamma * nv) * m) - V ;  gae = delta + (gamma_lambda * m) * gae   (no FMA)
+ * rewards/values/adv/ret fp32 [T][N], dones u8 [T][N], last_value fp32 [N]. */
+int kz_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_value,
+           int T, int N, float gamma, float gamma_lambda, float* adv, float* ret, void* stream);
+/* kz_gae dispatches on N: wide rollouts (N >= 2048) run one thread per env column, sequential in
+ * time, bit-exact with the reference's fp32 op order; narrow ones (the reference's N = 1 buffer)
+ * run one warp per column as a reverse affine-map warp scan (agrees to ~1e-6 relative).
+ * kz_gae_exact always takes the bit-exact column kernel. */
+int kz_gae_exact(const float* rewards, const float* values, const uint8_t* dones, const float* last_value,
+                 int T, int N, float gamma, float gamma_lambda, float* adv, float* ret, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

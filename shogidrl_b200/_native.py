@@ -1,0 +1,104 @@
+"""ctypes binding of the C-ABI library (include/keisei_b200.h).
+
+There is NO CPU fallback: if ``libkeisei_b200.so`` is missing or a CUDA device is not available the
+product path raises.  torch is used for device memory and streams only."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkeisei_b200.so")
+
+NUM_ACTIONS = 13527
+OBS_FLOATS = 46 * 81
+MASK_PAD_STRIDE = 13536
+REASONS = {0: None, 1: "Tsumi", 2: "stalemate", 3: "Max moves reached", 4: "Sennichite"}
+
+EXPORTS = [
+    "kz_abi_version", "kz_last_cuda_error", "kz_init_tables", "kz_state_layout", "kz_reset", "kz_load_positions",
+    "kz_export_positions", "kz_refresh", "kz_step", "kz_legal_mask", "kz_observe", "kz_errors", "kz_sample_masked",
+    "kz_gae", "kz_gae_exact",
+]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib: Optional[C.CDLL] = None
+_tables_ready = set()
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (never builds implicitly on a GPU box: the .so ships in-tree)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  shogidrl_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64, u32, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_float
+    L.kz_abi_version.restype = i32
+    L.kz_last_cuda_error.restype = C.c_char_p
+    L.kz_init_tables.argtypes = [vp]
+    L.kz_state_layout.argtypes = [i32, i32, C.POINTER(i64), C.POINTER(i64)]
+    L.kz_reset.argtypes = [vp, i32, i32, vp, i32, vp]
+    L.kz_load_positions.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.kz_export_positions.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+    L.kz_refresh.argtypes = [vp, i32, i32, vp, i64, vp, i64, vp, vp, i32, u64, u32, u32, i32, vp]
+    L.kz_step.argtypes = [vp, i32, i32, vp, i32, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, vp]
+    L.kz_legal_mask.argtypes = [vp, i32, i32, vp, i64, vp, vp]
+    L.kz_observe.argtypes = [vp, i32, i32, vp, i64, vp]
+    L.kz_errors.argtypes = [vp, i32, i32, vp, i32, vp]
+    L.kz_sample_masked.argtypes = [vp, i32, i64, vp, i64, i32, u64, u64, vp, i32, vp, vp, i32, vp]
+    L.kz_gae.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp, vp]
+    L.kz_gae_exact.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp, vp]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name not in ("kz_last_cuda_error",):
+            fn.restype = i32
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = {-1: "invalid argument", -2: "CUDA error: " + (lib().kz_last_cuda_error() or b"").decode(),
+               -3: "kz_init_tables has not run"}.get(rc, f"error {rc}")
+        raise NativeError(f"{what} failed: {msg}")
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(device) -> torch.device:
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise NativeError(f"shogidrl_b200 runs on CUDA devices only (got {device}); there is no CPU fallback")
+    if not torch.cuda.is_available():
+        raise NativeError("no CUDA device is available; shogidrl_b200 has no CPU fallback")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+def init_tables(device: torch.device) -> None:
+    """kz_init_tables once per device (ray / step tables, start-position bitmap)."""
+    device = require_cuda(device)
+    if device.index in _tables_ready:
+        return
+    with torch.cuda.device(device):
+        check(lib().kz_init_tables(stream_ptr(device)), "kz_init_tables")
+        torch.cuda.current_stream(device).synchronize()
+    _tables_ready.add(device.index)
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,1037 @@
+// kz_engine.cu -- sm_100a kernels for the Keisei self-play rollout hot path (engine part):
+// make_move + legal-move generation + termination + 13,527-byte legal mask + 46x9x9 observation,
+// one warp per game.
+//
+// Reference semantics implemented (paths relative to the reference checkout):
+//   keisei/shogi/shogi_rules_logic.py:82-208   pseudo-legal targets (steps, slides)
+//   keisei/shogi/shogi_rules_logic.py:486-635  legal moves = candidates whose mover's king is safe afterwards
+//   keisei/shogi/shogi_rules_logic.py:275-359  uchifuzume, :211-231 nifu, :382-483 promotion / drop rules
+//   keisei/shogi/shogi_game.py:408-450, 574-660 make_move, termination order, rewards
+//   keisei/shogi/shogi_game_io.py:434-539      observation planes
+//   keisei/utils/utils.py:208-266, 310-336     action enumeration and legal mask
+// The reference filters candidates by simulate-and-test; here the same set is computed from
+// checker / pin / king-danger bitboards built with warp ballots (lane l owns squares l, l+32, l+64, so
+// a ballot over slot j IS word j of an 81-bit bitboard).  tests/ check the two against each other.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/keisei_b200.h"
+#include "kz_common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// tables (filled by kz_init_tables): RAY[sq][dir] and STEP[class][sq] as 3-word bitboards
+__device__ uint32_t g_ray[81 * 8 * 3];
+__device__ uint32_t g_step[NCLS * 81 * 3];
+__device__ uint32_t g_init_bitmap[BITMAP_WORDS];  // legal bitmap of the start position (30 moves)
+__device__ int g_tables_ready = 0;
+
+__constant__ uint8_t c_init_board[96];
+
+struct __align__(16) WarpScratch {
+  uint32_t bitmap[BITMAP_WORDS];  // 13,527 legal bits in action-index order (+pad)
+  uint8_t board[96];
+  uint8_t meta[32];
+  uint8_t pind[2][96];    // [main/sub] pin direction per square, 0xFF = not pinned
+  uint32_t pinl[2][8 * 3];  // pin line per direction
+  uint8_t plist[2][40];   // squares of the mover's pieces
+  uint8_t dropv[96];      // 7 drop bits per square
+};
+
+struct Tables {
+  const uint32_t* ray;
+  const uint32_t* step;
+};
+
+__device__ __forceinline__ BB ld_ray(const Tables& T, int sq, int d) {
+  const uint32_t* p = T.ray + (sq * 8 + d) * 3;
+  return BB{p[0], p[1], p[2]};
+}
+__device__ __forceinline__ BB ld_step(const Tables& T, int cls, int sq) {
+  const uint32_t* p = T.step + (cls * 81 + sq) * 3;
+  return BB{p[0], p[1], p[2]};
+}
+
+// Targets of a slide from sq in direction d: up to and including the first occupied square
+// (shogi_rules_logic.py:194-206; own-colour blockers are removed by the caller).
+__device__ __forceinline__ BB slide_ray(const Tables& T, int sq, int d, BB occ) {
+  BB ray = ld_ray(T, sq, d);
+  BB bl = ray & occ;
+  if (bb_any(bl)) {
+    if (dir_positive(d)) ray = ray & bb_upto(bb_lsb(bl));
+    else ray = bb_andn(ray, bb_below(bb_msb(bl)));
+  }
+  return ray;
+}
+
+struct GenResult {
+  int count;
+  bool in_check;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Legal-move generation for side `me` on ws.board / hands.  EMIT: write the 13,527-bit legal bitmap;
+// otherwise count only (early exit as soon as one move is known).  skip_ufz: the is_escape_check mode
+// of can_drop_specific_piece (shogi_rules_logic.py:461-467).  ufz_all: test every pawn-drop square
+// for uchifuzume instead of only the square in front of the enemy king (needed only for loaded
+// positions in which the side NOT to move is already in check).
+template <bool EMIT>
+__device__ __noinline__ GenResult gen_moves(WarpScratch& ws, const Tables& T, const uint32_t tab, const int lane,
+                                            const int me, const uint8_t* hands, const bool skip_ufz,
+                                            const bool ufz_all);
+
+template <bool EMIT>
+__device__ __forceinline__ GenResult gen_moves_impl(WarpScratch& ws, const Tables& T, const uint32_t tab,
+                                                    const int lane, const int me, const uint8_t* hands,
+                                                    const bool skip_ufz, const bool ufz_all) {
+  constexpr int SCR = EMIT ? 0 : 1;  // scratch set: the count-only instance runs inside the emitting one
+  GenResult res;
+  res.count = 0;
+  res.in_check = false;
+
+  // ---- phase A: per-square view -> occupancy bitboards (ballots)
+  int c[3];
+  c[0] = ws.board[lane];
+  c[1] = ws.board[lane + 32];
+  c[2] = (lane < 17) ? ws.board[lane + 64] : 0;
+  BB occ, own;
+  int kcode = 8 + 14 * me, ekcode = 8 + 14 * (1 - me), pcode = 1 + 14 * me;
+  uint32_t kb[3], ekb[3];
+  uint32_t colbits = 0;
+  {
+    uint32_t o[3], w[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      o[j] = __ballot_sync(FULL, c[j] != 0);
+      w[j] = __ballot_sync(FULL, c[j] != 0 && code_color(c[j]) == me);
+      kb[j] = __ballot_sync(FULL, c[j] == kcode);
+      ekb[j] = __ballot_sync(FULL, c[j] == ekcode);
+      if (c[j] == pcode) colbits |= 1u << sq_col(lane + 32 * j);
+    }
+    occ = BB{o[0], o[1], o[2]};
+    own = BB{w[0], w[1], w[2]};
+  }
+  const uint32_t pawn_cols = __reduce_or_sync(FULL, colbits);  // nifu files (shogi_rules_logic.py:211-231)
+  const int K = (kb[0] | kb[1] | kb[2]) ? bb_lsb(BB{kb[0], kb[1], kb[2]}) : -1;   // find_king: first in row-major order
+  const int KE = (ekb[0] | ekb[1] | ekb[2]) ? bb_lsb(BB{ekb[0], ekb[1], ekb[2]}) : -1;
+
+  if (EMIT) {
+    uint4* bm = reinterpret_cast<uint4*>(ws.bitmap);
+    for (int i = lane; i < BITMAP_WORDS / 4; i += 32) bm[i] = make_uint4(0, 0, 0, 0);
+  }
+  ws.pind[SCR][lane] = 0xFF;
+  ws.pind[SCR][lane + 32] = 0xFF;
+  ws.pind[SCR][lane + 64] = 0xFF;
+  __syncwarp();
+
+  if (K < 0) {  // a missing king counts as "in check" and every candidate fails (shogi_rules_logic.py:370-373)
+    res.in_check = true;
+    return res;
+  }
+
+  // ---- phase B: checkers, pins (8 rays + 2 knight squares from the king), king-danger squares
+  const int fwd = me == 0 ? -1 : 1;
+  const int kr = sq_row(K), kc = K - 9 * kr;
+  int nchk;
+  BB CM;  // squares where a non-king move resolves a single check (checker square + squares between)
+  {
+    const int d = lane & 7;
+    const int od = (d + 4) & 7;
+    BB ray = ld_ray(T, K, d);
+    BB bl = ray & occ;
+    int b1 = -1, b2 = -1;
+    const bool pos = dir_positive(d);
+    if (bb_any(bl)) {
+      b1 = pos ? bb_lsb(bl) : bb_msb(bl);
+      BB bl2 = bb_andn(bl, bb_bit(b1));
+      if (bb_any(bl2)) b2 = pos ? bb_lsb(bl2) : bb_msb(bl2);
+    }
+    const int code1 = b1 >= 0 ? ws.board[b1] : 0;
+    const int code2 = b2 >= 0 ? ws.board[b2] : 0;
+    const uint32_t inf1 = __shfl_sync(FULL, tab, code1);
+    const uint32_t inf2 = __shfl_sync(FULL, tab, code2);
+    const bool adj = (b1 == K + dir_delta(d));
+    bool chk = false;
+    BB cm = BB{0, 0, 0};
+    if (lane < 8 && code1) {
+      if (code_color(code1) != me) {
+        if (((inf1 >> (8 + od)) & 1) || (adj && ((inf1 >> od) & 1))) {
+          chk = true;
+          BB between = pos ? (ray & bb_below(b1)) : bb_andn(ray, bb_upto(b1));
+          cm = between | bb_bit(b1);
+        }
+      } else if (code2 && code_color(code2) != me && ((inf2 >> (8 + od)) & 1)) {
+        // own piece b1 is pinned against the king by the slider on b2: it may only move along the ray up to b2
+        ws.pind[SCR][b1] = (uint8_t)d;
+        BB line = pos ? (ray & bb_upto(b2)) : bb_andn(ray, bb_below(b2));
+        ws.pinl[SCR][d * 3 + 0] = line.w0;
+        ws.pinl[SCR][d * 3 + 1] = line.w1;
+        ws.pinl[SCR][d * 3 + 2] = line.w2;
+      }
+    }
+    if (lane == 8 || lane == 9) {  // enemy knights: a knight on (r + 2*fwd, c +- 1) jumps onto the king
+      const int r = kr + 2 * fwd, cc = kc + (lane == 8 ? -1 : 1);
+      if (r >= 0 && r < 9 && cc >= 0 && cc < 9) {
+        const int s = r * 9 + cc;
+        if (ws.board[s] == 3 + 14 * (1 - me)) {
+          chk = true;
+          cm = bb_bit(s);
+        }
+      }
+    }
+    nchk = __popc(__ballot_sync(FULL, chk));
+    CM = BB{__reduce_or_sync(FULL, cm.w0), __reduce_or_sync(FULL, cm.w1), __reduce_or_sync(FULL, cm.w2)};
+  }
+  res.in_check = nchk > 0;
+
+  BB DANGER;  // king targets attacked by the enemy once the king has left its square
+  const BB kingsteps = ld_step(T, CLS_KING, K);
+  {
+    const BB occk = bb_andn(occ, bb_bit(K));
+    uint32_t attacked8 = 0;
+#pragma unroll
+    for (int round = 0; round < 2; round++) {
+      const int item = lane + 32 * round;
+      const int n = item >> 3, d = item & 7, od = (d + 4) & 7;
+      const int Tq = K + dir_delta(n);
+      const bool valid = Tq >= 0 && Tq < 81 && bb_test(kingsteps, Tq);
+      int code = 0, b = -1;
+      if (valid) {
+        BB bl = ld_ray(T, Tq, d) & occk;
+        if (bb_any(bl)) {
+          b = dir_positive(d) ? bb_lsb(bl) : bb_msb(bl);
+          code = ws.board[b];
+        }
+      }
+      const uint32_t inf = __shfl_sync(FULL, tab, code);
+      const bool att = code && code_color(code) != me &&
+                       (((inf >> (8 + od)) & 1) || (b == Tq + dir_delta(d) && ((inf >> od) & 1)));
+      const uint32_t bal = __ballot_sync(FULL, att);
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if ((bal >> (8 * q)) & 0xFF) attacked8 |= 1u << (round * 4 + q);
+    }
+    {
+      const int n = (lane >> 1) & 7;
+      const int Tq = K + dir_delta(n);
+      bool att = false;
+      if (lane < 16 && Tq >= 0 && Tq < 81 && bb_test(kingsteps, Tq)) {
+        const int tr = sq_row(Tq), tc = Tq - 9 * tr;
+        const int r = tr + 2 * fwd, cc = tc + ((lane & 1) ? 1 : -1);
+        if (r >= 0 && r < 9 && cc >= 0 && cc < 9) att = ws.board[r * 9 + cc] == 3 + 14 * (1 - me);
+      }
+      const uint32_t bal = __ballot_sync(FULL, att);
+#pragma unroll
+      for (int q = 0; q < 8; q++)
+        if ((bal >> (2 * q)) & 3) attacked8 |= 1u << q;
+    }
+    BB dg = BB{0, 0, 0};
+    if (lane < 8 && ((attacked8 >> lane) & 1)) dg = bb_bit(K + dir_delta(lane));
+    DANGER = BB{__reduce_or_sync(FULL, dg.w0), __reduce_or_sync(FULL, dg.w1), __reduce_or_sync(FULL, dg.w2)};
+  }
+  __syncwarp();
+
+  // ---- uchifuzume squares (shogi_rules_logic.py:275-359).  A dropped pawn gives check only from the
+  // square in front of the enemy king, unless that king is already attacked (loaded positions only).
+  BB UFZ = BB{0, 0, 0};
+  if constexpr (EMIT) {
+  if (!skip_ufz && hands[me * 7 + 0] > 0 && KE >= 0) {
+    const int last = me == 0 ? 0 : 8;
+    const int lo = ufz_all ? 0 : KE - 9 * fwd;
+    const int hi = ufz_all ? 80 : KE - 9 * fwd;
+    for (int D = lo; D <= hi; D++) {  // warp-uniform loop
+      if (D < 0 || D > 80) continue;
+      const int dr = sq_row(D), dc = D - 9 * dr;
+      if (ws.board[D] != 0 || dr == last || ((pawn_cols >> dc) & 1)) continue;
+      __syncwarp();
+      if (lane == 0) ws.board[D] = (uint8_t)pcode;
+      __syncwarp();
+      GenResult sub = gen_moves<false>(ws, T, tab, lane, 1 - me, hands, true, false);
+      __syncwarp();
+      if (lane == 0) ws.board[D] = 0;
+      __syncwarp();
+      if (sub.in_check && sub.count == 0) UFZ = UFZ | bb_bit(D);
+    }
+  }
+  }
+
+  // ---- phase C: board moves, one lane per own piece
+  int cnt = 0;
+  {
+    int nown = 0;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const uint32_t w = j == 0 ? own.w0 : (j == 1 ? own.w1 : own.w2);
+      if ((w >> lane) & 1) ws.plist[SCR][nown + __popc(w & ((1u << lane) - 1))] = (uint8_t)(lane + 32 * j);
+      nown += __popc(w);
+    }
+    __syncwarp();
+    const BB zone = me == 0 ? BB{0x07FFFFFFu, 0, 0} : BB{0, 0xFFC00000u, 0x0001FFFFu};       // rows 0-2 / rows 6-8
+    const BB last1 = me == 0 ? BB{0x000001FFu, 0, 0} : BB{0, 0, 0x0001FF00u};                 // row 0 / row 8
+    const BB last2 = me == 0 ? BB{0x0003FFFFu, 0, 0} : BB{0, 0x80000000u, 0x0001FFFFu};       // rows 0-1 / rows 7-8
+    for (int base = 0; base < nown; base += 32) {
+      const int i = base + lane;
+      const bool act = i < nown;
+      const int sq = act ? ws.plist[SCR][i] : 0;
+      const int code = act ? ws.board[sq] : 0;
+      const uint32_t inf = __shfl_sync(FULL, tab, code);
+      if (act) {
+        BB t = ld_step(T, (inf >> 16) & 15, sq);
+        uint32_t sl = (inf >> 8) & 0xFF;
+        while (sl) {
+          const int d = __ffs(sl) - 1;
+          sl &= sl - 1;
+          t = t | slide_ray(T, sq, d, occ);
+        }
+        t = bb_andn(t, own);
+        if ((inf >> 23) & 1) {
+          t = bb_andn(t, DANGER);
+        } else {
+          if (nchk >= 2) t = BB{0, 0, 0};
+          else if (nchk == 1) t = t & CM;
+          const int pd = ws.pind[SCR][sq];
+          if (pd != 0xFF) t = t & BB{ws.pinl[SCR][pd * 3], ws.pinl[SCR][pd * 3 + 1], ws.pinl[SCR][pd * 3 + 2]};
+        }
+        // promotion options (shogi_rules_logic.py:382-421, 509-519)
+        BB p = BB{0, 0, 0};
+        if ((inf >> 20) & 1) p = (me == 0 ? sq < 27 : sq >= 54) ? t : (t & zone);
+        const int mk = (inf >> 21) & 3;
+        BB np = t;
+        if (mk == 1) np = bb_andn(t, last1);
+        else if (mk == 2) np = bb_andn(t, last2);
+        cnt += bb_popc(np) + bb_popc(p);
+        if (EMIT) {
+          // drop the (always clear) self bit so that bit k is target k + (k >= from), then interleave
+          // no-promotion (even) and promotion (odd) bits: 160 bits = words [5*sq, 5*sq+5) of the bitmap
+          const BB lowm = bb_below(sq);
+          const BB npc = (np & lowm) | bb_andn(bb_shr1(np), lowm);
+          const BB pc = (p & lowm) | bb_andn(bb_shr1(p), lowm);
+          uint32_t* o = ws.bitmap + 5 * sq;
+          o[0] = spread16(npc.w0 & 0xFFFF) | (spread16(pc.w0 & 0xFFFF) << 1);
+          o[1] = spread16(npc.w0 >> 16) | (spread16(pc.w0 >> 16) << 1);
+          o[2] = spread16(npc.w1 & 0xFFFF) | (spread16(pc.w1 & 0xFFFF) << 1);
+          o[3] = spread16(npc.w1 >> 16) | (spread16(pc.w1 >> 16) << 1);
+          o[4] = spread16(npc.w2 & 0xFFFF) | (spread16(pc.w2 & 0xFFFF) << 1);
+        }
+      }
+    }
+  }
+  if (!EMIT) {  // count-only: a board move already settles "has a legal move"
+    if (__any_sync(FULL, cnt > 0)) {
+      res.count = 1;
+      return res;
+    }
+  }
+
+  // ---- phase D: drops, one lane per square (shogi_rules_logic.py:424-483, 561-629)
+  {
+    const int last = me == 0 ? 0 : 8, second = me == 0 ? 1 : 7;
+    const uint8_t* h = hands + me * 7;
+    const int hP = h[0], hL = h[1], hN = h[2], hS = h[3], hG = h[4], hB = h[5], hR = h[6];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const int sq = lane + 32 * j;
+      const uint32_t cmw = j == 0 ? CM.w0 : (j == 1 ? CM.w1 : CM.w2);
+      const uint32_t ufw = j == 0 ? UFZ.w0 : (j == 1 ? UFZ.w1 : UFZ.w2);
+      uint32_t v = 0;
+      if (sq < 81 && c[j] == 0 && nchk < 2 && (nchk == 0 || ((cmw >> lane) & 1))) {
+        const int r = sq_row(sq), col = sq - 9 * r;
+        if (hP > 0 && r != last && !((pawn_cols >> col) & 1) && !((ufw >> lane) & 1)) v |= 1;
+        if (hL > 0 && r != last) v |= 2;
+        if (hN > 0 && r != last && r != second) v |= 4;
+        if (hS > 0) v |= 8;
+        if (hG > 0) v |= 16;
+        if (hB > 0) v |= 32;
+        if (hR > 0) v |= 64;
+      }
+      cnt += __popc(v);
+      if (EMIT && sq < 96) ws.dropv[sq] = (uint8_t)v;
+    }
+  }
+  res.count = __reduce_add_sync(FULL, cnt);
+  if (EMIT) {
+    __syncwarp();
+    if (lane < 18) {  // bits 12960 + to*7 + type: word 405 + lane holds drop-stream bits [32*lane, 32*lane+32)
+      const int to0 = (32 * lane * 293) >> 11;  // floor(32*lane / 7)
+      int pos = 7 * to0 - 32 * lane;            // <= 0
+      uint32_t w = 0;
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        const int to = to0 + i;
+        const uint32_t v = to < 81 ? ws.dropv[to] : 0;
+        if (pos >= 0) { if (pos < 32) w |= v << pos; }
+        else w |= v >> (-pos);
+        pos += 7;
+      }
+      ws.bitmap[405 + lane] = w;
+    }
+    __syncwarp();
+  }
+  return res;
+}
+
+template <bool EMIT>
+__device__ __noinline__ GenResult gen_moves(WarpScratch& ws, const Tables& T, const uint32_t tab, const int lane,
+                                            const int me, const uint8_t* hands, const bool skip_ufz,
+                                            const bool ufz_all) {
+  return gen_moves_impl<EMIT>(ws, T, tab, lane, me, hands, skip_ufz, ufz_all);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 128-bit Zobrist-style key of (board, hands, side to move): four independent 32-bit tables realised as
+// hash functions of (square, code) / (hand slot, count).  Replaces the tuple of shogi_game.py:347-372.
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ uint4 zkey_item(uint32_t id) {
+  uint4 k;
+  k.x = fmix32(id * 0x9E3779B1u + 0x7F4A7C15u);
+  k.y = fmix32(id * 0x85EBCA77u + 0x165667B1u);
+  k.z = fmix32(id * 0xC2B2AE3Du + 0x27D4EB2Fu);
+  k.w = fmix32(id * 0x27D4EB2Fu + 0x9E3779B9u);
+  return k;
+}
+__device__ __forceinline__ uint4 position_key(const WarpScratch& ws, int lane, int side) {
+  uint4 k = make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const int sq = lane + 32 * j;
+    const int code = sq < 81 ? ws.board[sq] : 0;
+    if (code) { uint4 t = zkey_item(sq * 32 + code); k.x ^= t.x; k.y ^= t.y; k.z ^= t.z; k.w ^= t.w; }
+  }
+  if (lane < 14) {
+    const int cnt = ws.meta[lane];
+    if (cnt) { uint4 t = zkey_item(4096 + lane * 256 + cnt); k.x ^= t.x; k.y ^= t.y; k.z ^= t.z; k.w ^= t.w; }
+  }
+  if (lane == 31 && side) { uint4 t = zkey_item(8191); k.x ^= t.x; k.y ^= t.y; k.z ^= t.z; k.w ^= t.w; }
+  k.x = __reduce_xor_sync(FULL, k.x);
+  k.y = __reduce_xor_sync(FULL, k.y);
+  k.z = __reduce_xor_sync(FULL, k.z);
+  k.w = __reduce_xor_sync(FULL, k.w);
+  return k;
+}
+
+struct StepParams {
+  uint8_t* boards;
+  uint8_t* meta;
+  uint4* hist;
+  int hist_half;  // entries per parity array
+  int hist_cap;
+  int n;
+  const void* actions;
+  int actions_i64;
+  float* obs;
+  long long obs_stride;
+  uint8_t* mask;
+  long long mask_stride;
+  int mask_vec;  // 16-byte aligned rows: vector stores
+  float* reward;
+  uint8_t* done;
+  uint8_t* reason;
+  int8_t* winner;
+  int32_t* ep_len;
+  int32_t* legal_count;
+  void* next_actions;
+  unsigned long long seed;
+  uint32_t rng_step;
+  uint32_t env_offset;
+  int auto_reset;
+  int mode;  // 0 = refresh, 1 = step
+  int eval_term;
+};
+
+__device__ __forceinline__ uint32_t rand32(unsigned long long seed, unsigned long long env, unsigned long long step) {
+  unsigned long long x = seed ^ (env * 0x9E3779B97F4A7C15ull) ^ (step * 0xBF58476D1CE4E5B9ull);
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27; x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return (uint32_t)(x >> 32);
+}
+
+__device__ __forceinline__ uint16_t ld_u16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+__device__ __forceinline__ void st_u16(uint8_t* p, int v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) kz_step_kernel(const StepParams P) {
+  __shared__ uint32_t s_ray[81 * 8 * 3];
+  __shared__ uint32_t s_step[NCLS * 81 * 3];
+  __shared__ WarpScratch s_ws[WARPS_PER_CTA];
+  for (int i = threadIdx.x; i < 81 * 8 * 3; i += blockDim.x) s_ray[i] = g_ray[i];
+  for (int i = threadIdx.x; i < NCLS * 81 * 3; i += blockDim.x) s_step[i] = g_step[i];
+  __syncthreads();
+  const Tables T{s_ray, s_step};
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WarpScratch& ws = s_ws[warp];
+  const uint32_t tab = code_info(lane);
+
+  for (int g = blockIdx.x * WARPS_PER_CTA + warp; g < P.n; g += gridDim.x * WARPS_PER_CTA) {
+    // ---- load state
+    {
+      const uint32_t* bsrc = reinterpret_cast<const uint32_t*>(P.boards + (size_t)g * 96);
+      const uint32_t* msrc = reinterpret_cast<const uint32_t*>(P.meta + (size_t)g * 32);
+      if (lane < 24) reinterpret_cast<uint32_t*>(ws.board)[lane] = bsrc[lane];
+      else reinterpret_cast<uint32_t*>(ws.meta)[lane - 24] = msrc[lane - 24];
+    }
+    __syncwarp();
+    int side = ws.meta[14];
+    int status = ws.meta[15];
+    int winner = ws.meta[16] == 0xFF ? -1 : ws.meta[16];
+    int err = ws.meta[17];
+    int move_count = ld_u16(ws.meta + 18);
+    int hist_len = ld_u16(ws.meta + 20);
+    const int max_moves = ld_u16(ws.meta + 22);
+    uint32_t episodes = ws.meta[24] | (ws.meta[25] << 8) | (ws.meta[26] << 16) | (ws.meta[27] << 24);
+
+    float reward = 0.f;
+    int done_out = 0, reason_out = 0, winner_out = -1, ep_len_out = 0;
+    bool fresh_senn = false;
+    int mover = 1 - side;
+    bool moved = false;
+
+    if (P.mode == 1) {
+      long long a = P.actions_i64 ? reinterpret_cast<const long long*>(P.actions)[g]
+                                  : (long long)reinterpret_cast<const int*>(P.actions)[g];
+      if (status != 0) {
+        // make_move on a finished game returns the terminal tuple again (shogi_game.py:589-593)
+      } else if (a < 0 || a >= KZ_NUM_ACTIONS) {
+        err |= KZ_ERR_BAD_ACTION;
+      } else {
+        mover = side;
+        const int ai = (int)a;
+        bool ok = true;
+        if (ai < 12960) {
+          const int promo = ai & 1, pair = ai >> 1;
+          const int from = pair / 80, t80 = pair - from * 80, to = t80 + (t80 >= from);
+          const int code = ws.board[from], tcode = ws.board[to];
+          const uint32_t inf = __shfl_sync(FULL, tab, code);
+          if (!code || code_color(code) != side) { err |= KZ_ERR_BAD_ACTION; ok = false; }
+          else {
+            // movement-pattern validation only, as _validate_and_populate_board_move_details does
+            // (shogi_game.py:518-546): target must be in the piece's pseudo-legal set
+            uint32_t o0 = __ballot_sync(FULL, ws.board[lane] != 0), o1 = __ballot_sync(FULL, ws.board[lane + 32] != 0),
+                     o2 = __ballot_sync(FULL, lane < 17 && ws.board[lane + 64] != 0);
+            const BB occ{o0, o1, o2};
+            BB t = ld_step(T, (inf >> 16) & 15, from);
+            uint32_t sl = (inf >> 8) & 0xFF;
+            while (sl) { const int d = __ffs(sl) - 1; sl &= sl - 1; t = t | slide_ray(T, from, d, occ); }
+            if (!bb_test(t, to) || (tcode && code_color(tcode) == side) || (promo && !((inf >> 20) & 1))) {
+              err |= KZ_ERR_BAD_PATTERN; ok = false;
+            }
+          }
+          if (ok) {  // apply_move_to_board_state (shogi_move_execution.py:90-132)
+            __syncwarp();
+            if (lane == 0) {
+              if (tcode) {
+                const int tt = code_type(tcode);
+                if (tt == 7) err |= KZ_ERR_KING_CAPTURE;
+                else ws.meta[side * 7 + (tt >= 8 ? base_of_promoted(tt) : tt)] += 1;
+              }
+              ws.board[to] = (uint8_t)(promo ? code + promo_delta(code_type(code)) : code);
+              ws.board[from] = 0;
+            }
+            if (tcode && code_type(tcode) == 7) err |= KZ_ERR_KING_CAPTURE;
+          }
+        } else {
+          const int k = ai - 12960;
+          const int to = (k * 293) >> 11, pt = k - to * 7;
+          if (ws.board[to] != 0 || ws.meta[side * 7 + pt] == 0) { err |= KZ_ERR_BAD_ACTION; ok = false; }
+          if (ok) {  // drop (shogi_move_execution.py:55-71)
+            __syncwarp();
+            if (lane == 0) {
+              ws.board[to] = (uint8_t)(1 + pt + 14 * side);
+              ws.meta[side * 7 + pt] -= 1;
+            }
+          }
+        }
+        __syncwarp();
+        if (ok) {
+          moved = true;
+          move_count += 1;  // apply_move_to_game (shogi_move_execution.py:141-156)
+          side = 1 - side;
+          // history append + repetition count (shogi_game.py:651-654, shogi_rules_logic.py:680-695)
+          const uint4 key = position_key(ws, lane, side);
+          if (hist_len < P.hist_cap) {
+            uint4* hp = P.hist + ((size_t)g * 2 + (hist_len & 1)) * P.hist_half;
+            const int nprev = hist_len >> 1;
+            int matches = 0;
+            for (int i = lane; i < nprev; i += 32) {
+              const uint4 e = hp[i];
+              matches += (e.x == key.x && e.y == key.y && e.z == key.z && e.w == key.w);
+            }
+            matches = __reduce_add_sync(FULL, matches);
+            if (lane == 0) hp[nprev] = key;
+            fresh_senn = matches + 1 >= 4;
+            hist_len += 1;
+          } else {
+            err |= KZ_ERR_HISTORY_FULL;
+          }
+        }
+      }
+    }
+
+    // ---- legal moves of the position now on the board
+    const bool ufz_all = (P.mode == 0);  // loaded positions may have the side not to move in check
+    GenResult gr = gen_moves<true>(ws, T, tab, lane, side, ws.meta, false, false);
+    if (ufz_all) {
+      // anomaly test: only when the opponent's king is attacked can a pawn drop elsewhere "give check"
+      GenResult opp = gen_moves<false>(ws, T, tab, lane, 1 - side, ws.meta, true, false);
+      if (opp.in_check && ws.meta[side * 7] > 0) gr = gen_moves<true>(ws, T, tab, lane, side, ws.meta, false, true);
+    }
+
+    if ((moved || (P.mode == 0 && P.eval_term)) && status == 0) {
+      // _check_and_update_termination_status (shogi_game.py:408-450), in the reference's order
+      if (gr.count == 0) {
+        if (gr.in_check) { status = KZ_TSUMI; winner = mover; }
+        else { status = KZ_STALEMATE; winner = -1; }
+      } else if (move_count >= max_moves) { status = KZ_MAX_MOVES; winner = -1; }
+      else if (fresh_senn) { status = KZ_SENNICHITE; winner = -1; }
+    }
+    if (P.mode == 1 && status != 0) {  // _handle_real_move_return (shogi_game.py:553-572)
+      done_out = 1;
+      reason_out = status;
+      winner_out = winner;
+      ep_len_out = move_count;
+      if (winner >= 0) reward = winner == mover ? 1.f : -1.f;
+    }
+
+    if (P.mode == 1 && status != 0 && P.auto_reset) {
+      // StepManager.handle_episode_end -> game.reset() (step_manager.py:437-440; shogi_game.py:113-130)
+      __syncwarp();
+      if (lane < 24) reinterpret_cast<uint32_t*>(ws.board)[lane] = reinterpret_cast<const uint32_t*>(c_init_board)[lane];
+      if (lane < 14) ws.meta[lane] = 0;
+      side = 0; status = 0; winner = -1; move_count = 0; hist_len = 0;
+      episodes += 1;
+      for (int i = lane; i < BITMAP_WORDS; i += 32) ws.bitmap[i] = g_init_bitmap[i];
+      gr.count = 30;
+      gr.in_check = false;
+      __syncwarp();
+    }
+
+    // ---- outputs
+    if (lane == 0) {
+      if (P.reward) P.reward[g] = reward;
+      if (P.done) P.done[g] = (uint8_t)done_out;
+      if (P.reason) P.reason[g] = (uint8_t)reason_out;
+      if (P.winner) P.winner[g] = (int8_t)winner_out;
+      if (P.ep_len) P.ep_len[g] = ep_len_out;
+      if (P.legal_count) P.legal_count[g] = gr.count;
+    }
+
+    if (P.mask) {
+      uint8_t* mrow = P.mask + (size_t)g * P.mask_stride;
+      if (P.mask_vec) {
+        uint4* m4 = reinterpret_cast<uint4*>(mrow);
+        for (int q = lane; q < 846; q += 32) {
+          const uint32_t w = ws.bitmap[q >> 1];
+          const uint32_t b16 = (q & 1) ? (w >> 16) : (w & 0xFFFF);
+          uint4 v;
+          v.x = ((b16 & 0xF) * 0x00204081u) & 0x01010101u;
+          v.y = (((b16 >> 4) & 0xF) * 0x00204081u) & 0x01010101u;
+          v.z = (((b16 >> 8) & 0xF) * 0x00204081u) & 0x01010101u;
+          v.w = ((b16 >> 12) * 0x00204081u) & 0x01010101u;
+          if (q < 845 || P.mask_stride >= 13536) m4[q] = v;
+          else {  // last 7 bytes of an exactly-13,527-byte aligned row
+            const uint32_t parts[2] = {v.x, v.y};
+            for (int b = 0; b < 7; b++) mrow[13520 + b] = (uint8_t)(parts[b >> 2] >> (8 * (b & 3)));
+          }
+        }
+      } else {
+        for (int i = lane; i < KZ_NUM_ACTIONS; i += 32) mrow[i] = (uint8_t)((ws.bitmap[i >> 5] >> (i & 31)) & 1);
+      }
+    }
+
+    if (P.next_actions) {
+      long long pick = -1;
+      if (gr.count > 0) {
+        const uint32_t r = rand32(P.seed, (unsigned long long)P.env_offset + (unsigned long long)g, P.rng_step);
+        const int k = (int)(((unsigned long long)r * (unsigned long long)gr.count) >> 32);
+        // k-th set bit of the bitmap: lane owns words [14*lane, 14*lane+14)
+        int mycnt = 0;
+        const int w0 = lane * 14;
+        for (int i = 0; i < 14; i++) { const int w = w0 + i; if (w < 423) mycnt += __popc(ws.bitmap[w]); }
+        int incl = mycnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+        const int excl = incl - mycnt;
+        int found = -1;
+        if (k >= excl && k < incl) {
+          int rem = k - excl;
+          for (int i = 0; i < 14; i++) {
+            const uint32_t w = ws.bitmap[w0 + i];
+            const int pc = __popc(w);
+            if (rem < pc) { found = (w0 + i) * 32 + __fns(w, 0, rem + 1); break; }
+            rem -= pc;
+          }
+        }
+        const uint32_t who = __ballot_sync(FULL, found >= 0);
+        pick = __shfl_sync(FULL, found, __ffs(who) - 1);
+      }
+      if (lane == 0) {
+        if (P.actions_i64) reinterpret_cast<long long*>(P.next_actions)[g] = pick;
+        else reinterpret_cast<int*>(P.next_actions)[g] = (int)pick;
+      }
+    }
+
+    if (P.obs) {
+      // generate_neural_network_observation (shogi_game_io.py:434-539)
+      float* orow = P.obs + (size_t)g * P.obs_stride;
+      // constant planes 28..45: value of plane 28+i lives in lane i
+      float pv = 0.f;
+      if (lane < 14) {
+        const int cnt = ws.meta[lane < 7 ? side * 7 + lane : (1 - side) * 7 + (lane - 7)];
+        if (cnt > 0) pv = (float)((double)cnt / 18.0);
+      } else if (lane == 14) pv = side == 0 ? 1.f : 0.f;
+      else if (lane == 15) pv = max_moves > 0 ? (float)((double)move_count / (double)max_moves) : 0.f;
+      const int mis = ((uintptr_t)orow & 15) ? 2 : 0;  // rows are 8-byte aligned; odd rows start 8 past a 16-byte line
+      float4* o4 = reinterpret_cast<float4*>(orow + mis);
+      for (int it = 0; it < 30; it++) {  // 30 x 32 chunks >= 931; uniform trip count keeps the shuffles convergent
+        const int q = it * 32 + lane;
+        const int i0 = mis + 4 * q;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int x = i0 + e - 2268;
+          const int pl = x >= 0 ? ((x * 1619) >> 17) : 31;   // floor(x / 81); lane 31 holds 0
+          v[e] = __shfl_sync(FULL, pv, pl & 31);
+        }
+        if (q < 931) o4[q] = make_float4(v[0], v[1], v[2], v[3]);
+      }
+      if (lane == 0) {  // the 2 floats the float4 grid does not cover: plane 0 head or plane 45 tail, both 0 here
+        float2* o2 = reinterpret_cast<float2*>(orow + (mis ? 0 : 3724));
+        *o2 = make_float2(0.f, 0.f);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const int sq = lane + 32 * j;
+        const int code = sq < 81 ? ws.board[sq] : 0;
+        if (code) {
+          const int t = code_type(code), mine = code_color(code) == side;
+          const int plane = t < 8 ? (mine ? 0 : 14) + t : (mine ? 8 : 22) + (t - 8);
+          orow[plane * 81 + (side == 0 ? sq : 80 - sq)] = 1.0f;
+        }
+      }
+    }
+
+    // ---- store state
+    __syncwarp();
+    if (lane == 0) {
+      ws.meta[14] = (uint8_t)side;
+      ws.meta[15] = (uint8_t)status;
+      ws.meta[16] = (uint8_t)(winner < 0 ? 0xFF : winner);
+      ws.meta[17] = (uint8_t)err;
+      st_u16(ws.meta + 18, move_count);
+      st_u16(ws.meta + 20, hist_len);
+      ws.meta[24] = (uint8_t)episodes; ws.meta[25] = (uint8_t)(episodes >> 8);
+      ws.meta[26] = (uint8_t)(episodes >> 16); ws.meta[27] = (uint8_t)(episodes >> 24);
+    }
+    __syncwarp();
+    {
+      uint32_t* bdst = reinterpret_cast<uint32_t*>(P.boards + (size_t)g * 96);
+      uint32_t* mdst = reinterpret_cast<uint32_t*>(P.meta + (size_t)g * 32);
+      if (lane < 24) bdst[lane] = reinterpret_cast<uint32_t*>(ws.board)[lane];
+      else mdst[lane - 24] = reinterpret_cast<uint32_t*>(ws.meta)[lane - 24];
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void kz_reset_kernel(uint8_t* boards, uint8_t* meta, int n, const uint8_t* env_mask, int max_moves) {
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (g >= n) return;
+  if (env_mask && !env_mask[g]) return;
+  uint32_t* b = reinterpret_cast<uint32_t*>(boards + (size_t)g * 96);
+  uint32_t* m = reinterpret_cast<uint32_t*>(meta + (size_t)g * 32);
+  if (lane < 24) b[lane] = reinterpret_cast<const uint32_t*>(c_init_board)[lane];
+  else {
+    const int w = lane - 24;
+    uint32_t v = 0;
+    if (w == 4) v = 0xFFu;                                  // bytes 16..19: winner none, err 0, move_count 0
+    if (w == 5) v = ((uint32_t)max_moves & 0xFFFF) << 16;   // bytes 20..23: hist_len 0, max_moves
+    if (w == 6) v = m[6];                                   // keep the finished-episode counter
+    m[w] = v;
+  }
+}
+
+__global__ void kz_load_kernel(uint8_t* boards, uint8_t* meta, int n, const int8_t* src_b, const uint8_t* src_h,
+                               const uint8_t* src_side, const int32_t* src_mc, const int32_t* src_mm) {
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (g >= n) return;
+  uint8_t* b = boards + (size_t)g * 96;
+  uint8_t* m = meta + (size_t)g * 32;
+  for (int i = lane; i < 96; i += 32) b[i] = i < 81 ? (uint8_t)src_b[(size_t)g * 81 + i] : 0;
+  uint8_t v = 0;
+  if (lane < 14) v = src_h[(size_t)g * 14 + lane];
+  else if (lane == 14) v = src_side[g];
+  else if (lane == 16) v = 0xFF;
+  else if (lane == 18) v = (uint8_t)src_mc[g];
+  else if (lane == 19) v = (uint8_t)(src_mc[g] >> 8);
+  else if (lane == 22) v = (uint8_t)src_mm[g];
+  else if (lane == 23) v = (uint8_t)(src_mm[g] >> 8);
+  m[lane] = v;
+}
+
+__global__ void kz_export_kernel(const uint8_t* boards, const uint8_t* meta, int n, int8_t* dst_b, uint8_t* dst_h,
+                                 int32_t* dst_m) {
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (g >= n) return;
+  const uint8_t* b = boards + (size_t)g * 96;
+  const uint8_t* m = meta + (size_t)g * 32;
+  if (dst_b) for (int i = lane; i < 81; i += 32) dst_b[(size_t)g * 81 + i] = (int8_t)b[i];
+  if (dst_h && lane < 14) dst_h[(size_t)g * 14 + lane] = m[lane];
+  if (dst_m && lane < 8) {
+    int v = 0;
+    switch (lane) {
+      case 0: v = m[14]; break;
+      case 1: v = m[18] | (m[19] << 8); break;
+      case 2: v = m[22] | (m[23] << 8); break;
+      case 3: v = m[15]; break;
+      case 4: v = m[16] == 0xFF ? -1 : m[16]; break;
+      case 5: v = m[17]; break;
+      case 6: v = m[20] | (m[21] << 8); break;
+      case 7: v = m[24] | (m[25] << 8) | (m[26] << 16) | (m[27] << 24); break;
+    }
+    dst_m[(size_t)g * 8 + lane] = v;
+  }
+}
+
+__global__ void kz_errors_kernel(uint8_t* meta, int n, int32_t* out, int clear) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  out[g] = meta[(size_t)g * 32 + 17];
+  if (clear) meta[(size_t)g * 32 + 17] = 0;
+}
+
+thread_local char t_cuda_err[256] = "";
+int cuda_fail(cudaError_t e) {
+  snprintf(t_cuda_err, sizeof t_cuda_err, "%s", cudaGetErrorString(e));
+  return KZ_E_CUDA;
+}
+#define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return cuda_fail(_e); } while (0)
+
+int g_sm_count = 0;
+bool g_host_ready = false;
+
+struct Layout { int64_t off_boards, off_meta, off_hist, total; int hist_half; };
+Layout layout(int n, int hist_cap) {
+  Layout L;
+  L.hist_half = ((hist_cap + 1) / 2 + 3) & ~3;
+  L.off_boards = 0;
+  L.off_meta = (int64_t)n * 96;
+  L.off_hist = L.off_meta + (int64_t)n * 32;
+  L.off_hist = (L.off_hist + 255) & ~(int64_t)255;
+  L.total = L.off_hist + (int64_t)n * 2 * L.hist_half * 16;
+  return L;
+}
+
+int launch_step(void* state, int n, int hist_cap, StepParams P, cudaStream_t st) {
+  if (!state || n <= 0 || hist_cap < 0 || hist_cap > 65535) return KZ_E_ARG;
+  if (!g_host_ready) return KZ_E_NOT_INIT;
+  if (((uintptr_t)state & 255) != 0) return KZ_E_ARG;
+  const Layout L = layout(n, hist_cap);
+  uint8_t* base = reinterpret_cast<uint8_t*>(state);
+  P.boards = base + L.off_boards;
+  P.meta = base + L.off_meta;
+  P.hist = reinterpret_cast<uint4*>(base + L.off_hist);
+  P.hist_half = L.hist_half;
+  P.hist_cap = hist_cap;
+  P.n = n;
+  if (P.obs) {
+    if (((uintptr_t)P.obs & 15) || (P.obs_stride & 1) || P.obs_stride < KZ_OBS_FLOATS) return KZ_E_ARG;
+  }
+  P.mask_vec = 0;
+  if (P.mask) {
+    if (P.mask_stride < KZ_NUM_ACTIONS) return KZ_E_ARG;
+    P.mask_vec = (((uintptr_t)P.mask & 15) == 0 && (P.mask_stride & 15) == 0) ? 1 : 0;
+    if (n == 1 && ((uintptr_t)P.mask & 15) == 0) P.mask_vec = 1;
+  }
+  const int ctas_needed = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  int grid = g_sm_count * CTAS_PER_SM;
+  if (grid > ctas_needed) grid = ctas_needed;
+  kz_step_kernel<<<grid, WARPS_PER_CTA * 32, 0, st>>>(P);
+  CK(cudaGetLastError());
+  return KZ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kz_abi_version(void) { return KZ_ABI_VERSION; }
+const char* kz_last_cuda_error(void) { return t_cuda_err; }
+
+int kz_state_layout(int n, int hist_cap, int64_t* offsets3, int64_t* total_bytes) {
+  if (n <= 0 || hist_cap < 0 || hist_cap > 65535) return KZ_E_ARG;
+  const Layout L = layout(n, hist_cap);
+  if (offsets3) { offsets3[0] = L.off_boards; offsets3[1] = L.off_meta; offsets3[2] = L.off_hist; }
+  if (total_bytes) *total_bytes = L.total;
+  return KZ_OK;
+}
+
+int kz_init_tables(void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static const int DR[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
+  static const int DC[8] = {0, 1, 1, 1, 0, -1, -1, -1};
+  static uint32_t ray[81 * 8 * 3];
+  static uint32_t step[NCLS * 81 * 3];
+  memset(ray, 0, sizeof ray);
+  memset(step, 0, sizeof step);
+  auto setb = [](uint32_t* bb, int s) { bb[s >> 5] |= 1u << (s & 31); };
+  for (int s = 0; s < 81; s++) {
+    const int r = s / 9, c = s % 9;
+    for (int d = 0; d < 8; d++)
+      for (int k = 1; k < 9; k++) {
+        const int rr = r + DR[d] * k, cc = c + DC[d] * k;
+        if (rr < 0 || rr > 8 || cc < 0 || cc > 8) break;
+        setb(ray + (s * 8 + d) * 3, rr * 9 + cc);
+      }
+    // step classes: direction sets for BLACK (forward = N = dir 0); WHITE is the 180-degree rotation
+    const uint32_t P_ = 0x01, S_ = 0x01 | 0x02 | 0x80 | 0x08 | 0x20, G_ = 0x01 | 0x02 | 0x80 | 0x04 | 0x40 | 0x10;
+    const uint32_t PLUS_ = 0x55, X_ = 0xAA, K_ = 0xFF;
+    auto rot = [](uint32_t m) { return ((m << 4) | (m >> 4)) & 0xFF; };
+    const uint32_t dirsets[NCLS] = {P_, S_, G_, 0, rot(P_), rot(S_), rot(G_), 0, PLUS_, X_, K_, 0};
+    for (int cls = 0; cls < NCLS; cls++) {
+      uint32_t* bb = step + (cls * 81 + s) * 3;
+      for (int d = 0; d < 8; d++)
+        if ((dirsets[cls] >> d) & 1) {
+          const int rr = r + DR[d], cc = c + DC[d];
+          if (rr >= 0 && rr <= 8 && cc >= 0 && cc <= 8) setb(bb, rr * 9 + cc);
+        }
+      if (cls == CLS_BN || cls == CLS_WN) {  // knight: (2*forward, +-1) (shogi_rules_logic.py:121)
+        const int f = cls == CLS_BN ? -1 : 1;
+        for (int dc = -1; dc <= 1; dc += 2) {
+          const int rr = r + 2 * f, cc = c + dc;
+          if (rr >= 0 && rr <= 8 && cc >= 0 && cc <= 8) setb(bb, rr * 9 + cc);
+        }
+      }
+    }
+  }
+  // start position (shogi_game.py:79-111)
+  static uint8_t init[96];
+  memset(init, 0, sizeof init);
+  static const int back[9] = {1, 2, 3, 4, 7, 4, 3, 2, 1};
+  for (int c = 0; c < 9; c++) {
+    init[0 * 9 + c] = (uint8_t)(1 + back[c] + 14);
+    init[8 * 9 + c] = (uint8_t)(1 + back[c]);
+    init[2 * 9 + c] = (uint8_t)(1 + 0 + 14);
+    init[6 * 9 + c] = (uint8_t)(1 + 0);
+  }
+  init[1 * 9 + 1] = 1 + 6 + 14; init[1 * 9 + 7] = 1 + 5 + 14;
+  init[7 * 9 + 1] = 1 + 5;      init[7 * 9 + 7] = 1 + 6;
+  CK(cudaMemcpyToSymbolAsync(g_ray, ray, sizeof ray, 0, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyToSymbolAsync(g_step, step, sizeof step, 0, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyToSymbolAsync(c_init_board, init, sizeof init, 0, cudaMemcpyHostToDevice, st));
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  CK(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+  g_host_ready = true;
+  // legal bitmap of the start position, computed once by the engine itself on a scratch game
+  {
+    const Layout L = layout(1, 0);
+    void* scratch = nullptr;
+    CK(cudaMalloc(&scratch, L.total + KZ_MASK_PAD_STRIDE));
+    uint8_t* sb = reinterpret_cast<uint8_t*>(scratch);
+    kz_reset_kernel<<<1, 32, 0, st>>>(sb + L.off_boards, sb + L.off_meta, 1, nullptr, 500);
+    StepParams P{};
+    P.mask = sb + L.total;
+    P.mask_stride = KZ_MASK_PAD_STRIDE;
+    P.mode = 0;
+    int rc = launch_step(scratch, 1, 0, P, st);
+    if (rc != KZ_OK) { cudaFree(scratch); return rc; }
+    CK(cudaStreamSynchronize(st));
+    static uint8_t hm[KZ_MASK_PAD_STRIDE];
+    CK(cudaMemcpy(hm, sb + L.total, KZ_MASK_PAD_STRIDE, cudaMemcpyDeviceToHost));
+    static uint32_t bm[BITMAP_WORDS];
+    memset(bm, 0, sizeof bm);
+    for (int i = 0; i < KZ_NUM_ACTIONS; i++)
+      if (hm[i]) bm[i >> 5] |= 1u << (i & 31);
+    CK(cudaMemcpyToSymbol(g_init_bitmap, bm, sizeof bm));
+    CK(cudaFree(scratch));
+  }
+  return KZ_OK;
+}
+
+int kz_reset(void* state, int n, int hist_cap, const uint8_t* env_mask, int max_moves, void* stream) {
+  if (!state || n <= 0 || max_moves < 0 || max_moves > 65535) return KZ_E_ARG;
+  if (!g_host_ready) return KZ_E_NOT_INIT;
+  const Layout L = layout(n, hist_cap);
+  uint8_t* base = reinterpret_cast<uint8_t*>(state);
+  kz_reset_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(base + L.off_boards, base + L.off_meta, n,
+                                                                                   env_mask, max_moves);
+  CK(cudaGetLastError());
+  return KZ_OK;
+}
+
+int kz_load_positions(void* state, int n, int hist_cap, const int8_t* boards, const uint8_t* hands,
+                      const uint8_t* side, const int32_t* move_count, const int32_t* max_moves, void* stream) {
+  if (!state || n <= 0 || !boards || !hands || !side || !move_count || !max_moves) return KZ_E_ARG;
+  const Layout L = layout(n, hist_cap);
+  uint8_t* base = reinterpret_cast<uint8_t*>(state);
+  kz_load_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(base + L.off_boards, base + L.off_meta, n,
+                                                                                  boards, hands, side, move_count, max_moves);
+  CK(cudaGetLastError());
+  return KZ_OK;
+}
+
+int kz_export_positions(const void* state, int n, int hist_cap, int8_t* boards, uint8_t* hands, int32_t* meta8,
+                        void* stream) {
+  if (!state || n <= 0) return KZ_E_ARG;
+  const Layout L = layout(n, hist_cap);
+  const uint8_t* base = reinterpret_cast<const uint8_t*>(state);
+  kz_export_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(base + L.off_boards, base + L.off_meta, n,
+                                                                                    boards, hands, meta8);
+  CK(cudaGetLastError());
+  return KZ_OK;
+}
+
+int kz_errors(void* state, int n, int hist_cap, int32_t* out, int clear, void* stream) {
+  if (!state || n <= 0 || !out) return KZ_E_ARG;
+  const Layout L = layout(n, hist_cap);
+  uint8_t* base = reinterpret_cast<uint8_t*>(state);
+  kz_errors_kernel<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(base + L.off_meta, n, out, clear);
+  CK(cudaGetLastError());
+  return KZ_OK;
+}
+
+int kz_refresh(void* state, int n, int hist_cap, float* obs, int64_t obs_stride, uint8_t* mask, int64_t mask_stride,
+               int32_t* legal_count, void* next_actions, int actions_i64, uint64_t seed, uint32_t rng_step,
+               uint32_t env_offset, int eval_termination, void* stream) {
+  StepParams P{};
+  P.obs = obs; P.obs_stride = obs_stride; P.mask = mask; P.mask_stride = mask_stride;
+  P.legal_count = legal_count; P.next_actions = next_actions; P.actions_i64 = actions_i64;
+  P.seed = seed; P.rng_step = rng_step; P.env_offset = env_offset;
+  P.mode = 0; P.eval_term = eval_termination;
+  return launch_step(state, n, hist_cap, P, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int kz_step(void* state, int n, int hist_cap, const void* actions, int actions_i64, float* obs, int64_t obs_stride,
+            uint8_t* mask, int64_t mask_stride, float* reward, uint8_t* done, uint8_t* reason, int8_t* winner,
+            int32_t* ep_len, int32_t* legal_count, void* next_actions, uint64_t seed, uint32_t rng_step,
+            uint32_t env_offset, int auto_reset, void* stream) {
+  if (!actions) return KZ_E_ARG;
+  StepParams P{};
+  P.actions = actions; P.actions_i64 = actions_i64;
+  P.obs = obs; P.obs_stride = obs_stride; P.mask = mask; P.mask_stride = mask_stride;
+  P.reward = reward; P.done = done; P.reason = reason; P.winner = winner; P.ep_len = ep_len;
+  P.legal_count = legal_count; P.next_actions = next_actions;
+  P.seed = seed; P.rng_step = rng_step; P.env_offset = env_offset;
+  P.auto_reset = auto_reset; P.mode = 1;
+  return launch_step(state, n, hist_cap, P, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int kz_legal_mask(void* state, int n, int hist_cap, uint8_t* mask, int64_t mask_stride, int32_t* legal_count,
+                  void* stream) {
+  if (!mask && !legal_count) return KZ_E_ARG;
+  return kz_refresh(state, n, hist_cap, nullptr, 0, mask, mask_stride, legal_count, nullptr, 0, 0, 0, 0, 0, stream);
+}
+
+int kz_observe(void* state, int n, int hist_cap, float* obs, int64_t obs_stride, void* stream) {
+  if (!obs) return KZ_E_ARG;
+  return kz_refresh(state, n, hist_cap, obs, obs_stride, nullptr, 0, nullptr, nullptr, 0, 0, 0, 0, 0, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,243 @@
+// kz_rl.cu -- sm_100a kernels for the agent/buffer side of the rollout hot path:
+//   kz_sample_masked : masked softmax -> Categorical sample / argmax -> log_prob (+ entropy)
+//                      (keisei/core/base_actor_critic.py:64-116; torch.distributions.Categorical(probs=...))
+//   kz_gae           : reverse-time GAE over a [T][N] rollout (keisei/core/experience_buffer.py:99-145)
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <float.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/keisei_b200.h"
+
+#define FULL 0xffffffffu
+
+namespace {
+
+thread_local char t_err[256] = "";
+int fail(cudaError_t e) {
+  snprintf(t_err, sizeof t_err, "%s", cudaGetErrorString(e));
+  return KZ_E_CUDA;
+}
+
+__device__ __forceinline__ float ld_logit(const void* row, int i, int bf16) {
+  return bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(row)[i]) : reinterpret_cast<const float*>(row)[i];
+}
+
+__device__ __forceinline__ uint32_t hash_u32(unsigned long long seed, unsigned long long ctr) {
+  unsigned long long x = seed ^ (ctr * 0x9E3779B97F4A7C15ull) ^ 0xD1B54A32D192ED03ull;
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27; x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return (uint32_t)(x >> 32);
+}
+
+// One warp per row.  Element order for the inverse CDF: lane-major (lane 0's elements 0,32,64,..., then
+// lane 1's, ...), a fixed permutation of the action axis, so the sampled law is the masked softmax.
+__global__ void __launch_bounds__(256) kz_sample_kernel(const void* logits, int bf16, long long ld, const uint8_t* mask,
+                                                        long long ldm, int n, unsigned long long seed,
+                                                        unsigned long long offset, void* actions, int actions_i64,
+                                                        float* logp, float* entropy, int deterministic) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const char* lrow = reinterpret_cast<const char*>(logits) + (size_t)row * ld * (bf16 ? 2 : 4);
+  const uint8_t* mrow = mask + (size_t)row * ldm;
+  const int A = KZ_NUM_ACTIONS;
+
+  // pass 1: online max / sum of exp over legal entries; track the per-lane argmax (lowest index on ties)
+  float m = -INFINITY, s = 0.f;
+  int amax = -1;
+  for (int i = lane; i < A; i += 32) {
+    if (mrow[i]) {
+      const float x = ld_logit(lrow, i, bf16);
+      if (x > m) { s = s * expf(m - x) + 1.f; m = x; amax = i; }
+      else s += expf(x - m);
+    }
+  }
+  float M = m;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) M = fmaxf(M, __shfl_xor_sync(FULL, M, o));
+  const bool any_legal = M > -INFINITY || __any_sync(FULL, amax >= 0);
+  long long act = -1;
+  float lp = 0.f, ent = 0.f;
+  if (!any_legal || !(M > -INFINITY)) {
+    // no legal entry (or all legal logits are -inf): softmax is NaN -> uniform over all actions
+    // (base_actor_critic.py:93-101)
+    const float p = 1.0f / (float)A;
+    if (deterministic) act = 0;
+    else act = (long long)(((unsigned long long)hash_u32(seed, offset + row) * (unsigned long long)A) >> 32);
+    lp = logf(p);
+    ent = -logf(p);
+  } else {
+    const float mys = (m > -INFINITY) ? s * expf(m - M) : 0.f;  // this lane's sum rescaled to the row max
+    float tot = mys;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
+    const float inv = 1.0f / tot;
+    int pick = -1;
+    if (deterministic) {
+      // argmax of probs == argmax of legal logits; lowest index wins ties
+      int cand = (m == M) ? amax : 0x7fffffff;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) cand = min(cand, __shfl_xor_sync(FULL, cand, o));
+      pick = cand;
+    } else {
+      const float u = (float)(hash_u32(seed, offset + row) >> 8) * (1.0f / 16777216.0f);
+      const float target = u * tot;
+      // lane prefix
+      float incl = mys;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+      const uint32_t hit = __ballot_sync(FULL, incl > target && mys > 0.f);
+      int L = hit ? __ffs(hit) - 1 : -1;
+      if (L < 0) {  // rounding pushed the target past the total: take the last lane that has mass
+        const uint32_t have = __ballot_sync(FULL, mys > 0.f);
+        L = 31 - __clz(have);
+      }
+      const float base = __shfl_sync(FULL, incl - mys, L);
+      // walk lane L's elements (L, L+32, ...) 32 at a time
+      float run = base;
+      int lastlegal = -1;
+      for (int j0 = 0; j0 * 32 + L < A && pick < 0; j0 += 32) {
+        const int i = (j0 + lane) * 32 + L;
+        float e = 0.f;
+        if (i < A && mrow[i]) e = expf(ld_logit(lrow, i, bf16) - M);
+        float sc = e;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(FULL, sc, o); if (lane >= o) sc += t; }
+        const uint32_t h = __ballot_sync(FULL, e > 0.f && run + sc > target);
+        const uint32_t lg = __ballot_sync(FULL, e > 0.f);
+        if (h) pick = (j0 + __ffs(h) - 1) * 32 + L;
+        if (lg) lastlegal = (j0 + 31 - __clz(lg)) * 32 + L;
+        run += __shfl_sync(FULL, sc, 31);
+      }
+      if (pick < 0) pick = lastlegal;
+    }
+    act = pick;
+    // Categorical(probs=p): logits = log(clamp(p, eps, 1 - eps)) with eps = FLT_EPSILON
+    const float eps = FLT_EPSILON;
+    if (lane == 0) {
+      const float p = expf(ld_logit(lrow, pick, bf16) - M) * inv;
+      lp = logf(fminf(fmaxf(p, eps), 1.0f - eps));
+    }
+    if (entropy) {
+      float h = 0.f;
+      for (int i = lane; i < A; i += 32)
+        if (mrow[i]) {
+          const float p = expf(ld_logit(lrow, i, bf16) - M) * inv;
+          h -= p * logf(fminf(fmaxf(p, eps), 1.0f - eps));
+        }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) h += __shfl_xor_sync(FULL, h, o);
+      ent = h;
+    }
+  }
+  if (lane == 0) {
+    if (actions_i64) reinterpret_cast<long long*>(actions)[row] = act;
+    else reinterpret_cast<int*>(actions)[row] = (int)act;
+    if (logp) logp[row] = lp;
+    if (entropy) entropy[row] = ent;
+  }
+}
+
+// GAE, exact variant: one thread per env column, sequential over time in the reference's op order with
+// every operation rounded separately (__fmul_rn/__fadd_rn are never contracted into FMAs).  Loads are
+// coalesced across envs.  Used when N offers enough parallelism.
+__global__ void kz_gae_columns_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
+                                      const uint8_t* __restrict__ dones, const float* __restrict__ last_value, int T,
+                                      int N, float gamma, float gl, float* __restrict__ adv, float* __restrict__ ret) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float gae = 0.f;
+  float nv = last_value[n];
+#pragma unroll 4
+  for (int t = T - 1; t >= 0; t--) {
+    const size_t i = (size_t)t * N + n;
+    const float r = rewards[i], v = values[i];
+    const float m = dones[i] ? 0.f : 1.f;
+    const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(gamma, nv), m)), v);
+    gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, m), gae));
+    adv[i] = gae;
+    ret[i] = __fadd_rn(gae, v);
+    nv = v;
+  }
+}
+
+// GAE, warp-scan variant for narrow rollouts (small N, e.g. the reference's flat N = 1 buffer): one warp
+// per env column, 32 timesteps per round processed as a reverse inclusive scan over the affine maps
+// gae_t = delta_t + c_t * gae_{t+1}.  Composition reassociates the fp32 products, so this variant agrees
+// with the sequential order to ~1e-6 relative (north-star tolerance 1e-5), not bit-for-bit.
+__global__ void kz_gae_warpscan_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
+                                       const uint8_t* __restrict__ dones, const float* __restrict__ last_value, int T,
+                                       int N, float gamma, float gl, float* __restrict__ adv, float* __restrict__ ret) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  float carry = 0.f;  // gae_{t+1} entering the current round
+  for (int hi = T - 1; hi >= 0; hi -= 32) {
+    const int t = hi - lane;  // lane 0 = latest timestep of the round
+    float a = 1.f, b = 0.f, v = 0.f;
+    if (t >= 0) {
+      const size_t i = (size_t)t * N + n;
+      v = values[i];
+      const float m = dones[i] ? 0.f : 1.f;
+      const float nv = (t == T - 1) ? last_value[n] : values[i + N];
+      b = __fsub_rn(__fadd_rn(rewards[i], __fmul_rn(__fmul_rn(gamma, nv), m)), v);  // delta_t
+      a = __fmul_rn(gl, m);                                                          // c_t
+    }
+    // inclusive scan in lane order (= reverse time): f_lane o f_{lane-1} o ... o f_0
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float pa = __shfl_up_sync(FULL, a, o), pb = __shfl_up_sync(FULL, b, o);
+      if (lane >= o) { b = fmaf(a, pb, b); a = a * pa; }
+    }
+    const float g = fmaf(a, carry, b);
+    if (t >= 0) {
+      const size_t i = (size_t)t * N + n;
+      adv[i] = g;
+      ret[i] = g + v;
+    }
+    carry = __shfl_sync(FULL, g, 31);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int kz_sample_masked(const void* logits, int logits_bf16, int64_t ld, const uint8_t* mask, int64_t ldm, int n,
+                     uint64_t seed, uint64_t offset, void* actions, int actions_i64, float* logp, float* entropy,
+                     int deterministic, void* stream) {
+  if (!logits || !mask || !actions || n <= 0 || ld < KZ_NUM_ACTIONS || ldm < KZ_NUM_ACTIONS) return KZ_E_ARG;
+  kz_sample_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      logits, logits_bf16, ld, mask, ldm, n, seed, offset, actions, actions_i64, logp, entropy, deterministic);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? KZ_OK : fail(e);
+}
+
+int kz_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_value, int T, int N,
+           float gamma, float gamma_lambda, float* adv, float* ret, void* stream) {
+  if (!rewards || !values || !dones || !last_value || !adv || !ret || T <= 0 || N <= 0) return KZ_E_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (N >= 2048) {
+    kz_gae_columns_kernel<<<(N + 127) / 128, 128, 0, st>>>(rewards, values, dones, last_value, T, N, gamma, gamma_lambda,
+                                                           adv, ret);
+  } else {
+    kz_gae_warpscan_kernel<<<(N + 3) / 4, 128, 0, st>>>(rewards, values, dones, last_value, T, N, gamma, gamma_lambda, adv,
+                                                        ret);
+  }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? KZ_OK : fail(e);
+}
+
+/* exact column kernel regardless of N (tests / bit-exact comparisons) */
+int kz_gae_exact(const float* rewards, const float* values, const uint8_t* dones, const float* last_value, int T, int N,
+                 float gamma, float gamma_lambda, float* adv, float* ret, void* stream) {
+  if (!rewards || !values || !dones || !last_value || !adv || !ret || T <= 0 || N <= 0) return KZ_E_ARG;
+  kz_gae_columns_kernel<<<(N + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      rewards, values, dones, last_value, T, N, gamma, gamma_lambda, adv, ret);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? KZ_OK : fail(e);
+}
+
+}  // extern "C"

@@ -1,0 +1,146 @@
+"""VecShogiEnv -- N device-resident Shogi games stepped by one kernel launch.
+
+Batched counterpart of ``keisei.shogi.ShogiGame`` + the reset-on-done handling of
+``keisei.training.step_manager.StepManager`` (step_manager.py:98-348, 437-440).  All arrays live on the
+GPU; observations and masks are written by the kernel straight into caller-provided rollout storage."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _native as nv
+
+
+class VecShogiEnv:
+    def __init__(self, num_envs: int, max_moves_per_game: int = 500, device="cuda", seed: int = 1234,
+                 env_offset: int = 0, auto_reset: bool = True, hist_cap: Optional[int] = None):
+        self.device = nv.require_cuda(device)
+        self.n = int(num_envs)
+        self.max_moves = int(max_moves_per_game)
+        self.hist_cap = int(hist_cap if hist_cap is not None else max_moves_per_game)
+        self.seed = int(seed)
+        self.env_offset = int(env_offset)
+        self.auto_reset = bool(auto_reset)
+        self._L = nv.lib()
+        nv.init_tables(self.device)
+        offs = (C.c_int64 * 3)()
+        total = C.c_int64()
+        nv.check(self._L.kz_state_layout(self.n, self.hist_cap, offs, C.byref(total)), "kz_state_layout")
+        self.state = torch.zeros(total.value, dtype=torch.uint8, device=self.device)
+        self.state_bytes = total.value
+        # persistent per-step outputs
+        d = self.device
+        self.obs = torch.zeros((self.n, 46, 9, 9), dtype=torch.float32, device=d)
+        self._mask_store = torch.zeros((self.n, nv.MASK_PAD_STRIDE), dtype=torch.uint8, device=d)
+        self.mask = self._mask_store[:, : nv.NUM_ACTIONS]  # uint8 view, row stride 13536
+        self.reward = torch.zeros(self.n, dtype=torch.float32, device=d)
+        self.done = torch.zeros(self.n, dtype=torch.uint8, device=d)
+        self.reason = torch.zeros(self.n, dtype=torch.uint8, device=d)
+        self.winner = torch.zeros(self.n, dtype=torch.int8, device=d)
+        self.ep_len = torch.zeros(self.n, dtype=torch.int32, device=d)
+        self.legal_count = torch.zeros(self.n, dtype=torch.int32, device=d)
+        self.next_actions = torch.zeros(self.n, dtype=torch.int64, device=d)
+        self.step_index = 0
+        self.reset()
+
+    # ------------------------------------------------------------------ helpers
+    def _sp(self):
+        return nv.stream_ptr(self.device)
+
+    @staticmethod
+    def _obs_args(obs: Optional[torch.Tensor]):
+        if obs is None:
+            return None, 0
+        assert obs.dtype == torch.float32 and obs.stride(-1) == 1
+        return obs.data_ptr(), (obs.stride(0) if obs.dim() > 1 else nv.OBS_FLOATS)
+
+    @staticmethod
+    def _mask_args(mask: Optional[torch.Tensor]):
+        if mask is None:
+            return None, 0
+        assert mask.dtype in (torch.uint8, torch.bool) and mask.stride(-1) == 1
+        return mask.data_ptr(), (mask.stride(0) if mask.dim() > 1 else nv.NUM_ACTIONS)
+
+    # ------------------------------------------------------------------ API
+    def reset(self, env_mask: Optional[torch.Tensor] = None, refresh: bool = True, random_actions: bool = False):
+        """ShogiGame.reset for all (or the masked) envs; returns (obs, mask) of the new positions."""
+        mp = None
+        if env_mask is not None:
+            env_mask = env_mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            mp = env_mask.data_ptr()
+        nv.check(self._L.kz_reset(self.state.data_ptr(), self.n, self.hist_cap, mp, self.max_moves, self._sp()), "kz_reset")
+        if env_mask is None:
+            self.step_index = 0
+        if refresh:
+            self.refresh(random_actions=random_actions)
+        return self.obs, self.mask
+
+    def refresh(self, obs: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
+                eval_termination: bool = False, random_actions: bool = False):
+        """Recompute obs / mask / legal_count (and optionally uniform-random legal actions) in place."""
+        obs = self.obs if obs is None else obs
+        mask = self.mask if mask is None else mask
+        op, os_ = self._obs_args(obs)
+        mp, ms = self._mask_args(mask)
+        nv.check(self._L.kz_refresh(self.state.data_ptr(), self.n, self.hist_cap, op, os_, mp, ms,
+                                    self.legal_count.data_ptr(), self.next_actions.data_ptr() if random_actions else None,
+                                    1, self.seed, self.step_index, self.env_offset, int(eval_termination), self._sp()),
+                 "kz_refresh")
+        return obs, mask
+
+    def step(self, actions: torch.Tensor, obs: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
+             random_actions: bool = False, write_obs: bool = True, write_mask: bool = True) -> Dict[str, torch.Tensor]:
+        """make_move for every env.  ``obs`` / ``mask`` may point into a rollout buffer (e.g. obs_buf[t+1])."""
+        assert actions.device == self.device and actions.dtype in (torch.int64, torch.int32) and actions.is_contiguous()
+        obs = (self.obs if obs is None else obs) if write_obs else None
+        mask = (self.mask if mask is None else mask) if write_mask else None
+        op, os_ = self._obs_args(obs)
+        mp, ms = self._mask_args(mask)
+        self.step_index += 1
+        nxt = None
+        if random_actions:
+            nxt = self.next_actions if actions.dtype == torch.int64 else self.next_actions.view(torch.int32)[: self.n]
+        nv.check(self._L.kz_step(self.state.data_ptr(), self.n, self.hist_cap, actions.data_ptr(),
+                                 int(actions.dtype == torch.int64), op, os_, mp, ms, self.reward.data_ptr(),
+                                 self.done.data_ptr(), self.reason.data_ptr(), self.winner.data_ptr(),
+                                 self.ep_len.data_ptr(), self.legal_count.data_ptr(),
+                                 nxt.data_ptr() if nxt is not None else None, self.seed, self.step_index,
+                                 self.env_offset, int(self.auto_reset), self._sp()), "kz_step")
+        return {"obs": obs, "mask": mask, "reward": self.reward, "done": self.done, "reason": self.reason,
+                "winner": self.winner, "ep_len": self.ep_len, "legal_count": self.legal_count}
+
+    def load_positions(self, boards, hands, side, move_count, max_moves=None, eval_termination: bool = True):
+        """ShogiGame.from_sfen for every env from already-parsed arrays (numpy or torch)."""
+        d = self.device
+        b = torch.as_tensor(np.ascontiguousarray(boards), dtype=torch.int8).to(d).contiguous()
+        h = torch.as_tensor(np.ascontiguousarray(hands), dtype=torch.uint8).to(d).contiguous()
+        s = torch.as_tensor(np.ascontiguousarray(side), dtype=torch.uint8).to(d).contiguous()
+        mc = torch.as_tensor(np.ascontiguousarray(move_count), dtype=torch.int32).to(d).contiguous()
+        if max_moves is None:
+            max_moves = np.full(self.n, self.max_moves, np.int32)
+        mm = torch.as_tensor(np.ascontiguousarray(max_moves), dtype=torch.int32).to(d).contiguous()
+        assert b.shape == (self.n, 81) and h.shape == (self.n, 14)
+        nv.check(self._L.kz_load_positions(self.state.data_ptr(), self.n, self.hist_cap, b.data_ptr(), h.data_ptr(),
+                                           s.data_ptr(), mc.data_ptr(), mm.data_ptr(), self._sp()), "kz_load_positions")
+        self.refresh(eval_termination=eval_termination)
+        return self.obs, self.mask
+
+    def export(self):
+        """-> boards int8 [n,81], hands uint8 [n,14], meta int32 [n,8] (side, move_count, max_moves, status,
+        winner, error bits, plies since reset, finished episodes) as torch tensors on the device."""
+        d = self.device
+        b = torch.empty((self.n, 81), dtype=torch.int8, device=d)
+        h = torch.empty((self.n, 14), dtype=torch.uint8, device=d)
+        m = torch.empty((self.n, 8), dtype=torch.int32, device=d)
+        nv.check(self._L.kz_export_positions(self.state.data_ptr(), self.n, self.hist_cap, b.data_ptr(), h.data_ptr(),
+                                             m.data_ptr(), self._sp()), "kz_export_positions")
+        return b, h, m
+
+    def errors(self, clear: bool = False) -> torch.Tensor:
+        out = torch.empty(self.n, dtype=torch.int32, device=self.device)
+        nv.check(self._L.kz_errors(self.state.data_ptr(), self.n, self.hist_cap, out.data_ptr(), int(clear), self._sp()),
+                 "kz_errors")
+        return out

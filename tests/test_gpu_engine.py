@@ -1,0 +1,236 @@
+"""GPU parity tests of the engine kernels (kz_step / kz_refresh) through the C ABI.
+
+Checked against (a) golden traces produced by the Python reference itself (tests/golden/) and
+(b) the C oracle (oracle/) on the same seeded inputs.  Bit-exact: legal sets, masks, successor
+boards / hands / side / move_count, rewards, dones, reasons, winners, observation tensors."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as orc  # noqa: E402  (checker only)
+
+
+def _digest(obs_row: np.ndarray) -> int:
+    return int.from_bytes(hashlib.blake2b(np.ascontiguousarray(obs_row, np.float32).tobytes(), digest_size=8).digest(), "little")
+
+
+def _fmt_pos(board, hands, side):
+    sym = "PLNSGBRK"
+    rows = []
+    for r in range(9):
+        row = []
+        for c in range(9):
+            code = int(board[r * 9 + c])
+            if code == 0:
+                row.append(" . ")
+            else:
+                t, col = (code - 1) % 14, (code - 1) // 14
+                s = ("+" + sym[{8: 0, 9: 1, 10: 2, 11: 3, 12: 5, 13: 6}[t]]) if t >= 8 else (" " + sym[t])
+                row.append((s.lower() if col else s) + " ")
+        rows.append("".join(row))
+    return "\n".join(rows) + f"\nhands B={list(hands[:7])} W={list(hands[7:])} side={side}"
+
+
+def _explain(board, hands, side, got_idx, want_idx):
+    got, want = set(int(x) for x in got_idx), set(int(x) for x in want_idx)
+    return (f"\n{_fmt_pos(board, hands, side)}\nGPU-only: {[orc.index_to_move(i) for i in sorted(got - want)]}"
+            f"\nreference-only: {[orc.index_to_move(i) for i in sorted(want - got)]}")
+
+
+@pytest.fixture(scope="module")
+def traces(golden_dir):
+    with np.load(os.path.join(golden_dir, "traces_random.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def _replay_group(z, games, dev):
+    """Replay the golden games `games` (same T and max_moves) in one device batch, auto_reset off."""
+    from shogidrl_b200 import VecShogiEnv
+
+    n = len(games)
+    T, mm = int(z["T"][games[0]]), int(z["max_moves"][games[0]])
+    starts = np.concatenate([[0], np.cumsum(z["T"])])[:-1]
+    env = VecShogiEnv(n, max_moves_per_game=mm, device=dev, auto_reset=False)
+    for t in range(T):
+        ix = [int(starts[g]) + t for g in games]
+        mask = env.mask.cpu().numpy()
+        b, h, m = [x.cpu().numpy() for x in env.export()]
+        for e, i in enumerate(ix):
+            want = z["legal"][z["legal_off"][i]:z["legal_off"][i + 1]].astype(np.int64)
+            got = np.nonzero(mask[e])[0]
+            assert np.array_equal(got, want), (games[e], t, _explain(b[e], h[e], m[e, 0], got, want))
+            assert int(env.legal_count[e]) == len(want)
+        acts = torch.as_tensor(z["actions"][ix].astype(np.int64), device=dev)
+        out = env.step(acts)
+        torch.cuda.synchronize()
+        assert int(env.errors().abs().sum()) == 0
+        b, h, m = [x.cpu().numpy() for x in env.export()]
+        obs = out["obs"].cpu().numpy()
+        assert np.array_equal(b, z["boards"][ix]), (t,)
+        assert np.array_equal(h, z["hands"][ix]), (t,)
+        assert np.array_equal(m[:, 0], z["sides"][ix]) and np.array_equal(m[:, 1], z["move_counts"][ix]), (t,)
+        assert np.array_equal(out["reward"].cpu().numpy(), z["rewards"][ix]), (t,)
+        assert np.array_equal(out["done"].cpu().numpy(), z["dones"][ix]), (t, out["reason"].cpu().numpy(), z["reasons"][ix])
+        assert np.array_equal(out["reason"].cpu().numpy(), z["reasons"][ix]), (t,)
+        assert np.array_equal(out["winner"].cpu().numpy(), z["winners"][ix]), (t,)
+        for e, i in enumerate(ix):
+            assert _digest(obs[e]) == int(z["digests"][i]), (games[e], t)
+        d = out["done"].bool()
+        if bool(d.any()):
+            env.reset(env_mask=d)  # what StepManager.handle_episode_end does (step_manager.py:437-440)
+    return n * T
+
+
+def test_golden_traces_replay(traces):
+    """Every ply of the Python reference's own random-play games, replayed on the GPU."""
+    dev = torch.device("cuda:0")
+    z = traces
+    total = 0
+    groups = {}
+    for g in range(len(z["env"])):
+        groups.setdefault((int(z["T"][g]), int(z["max_moves"][g])), []).append(g)
+    for games in groups.values():
+        total += _replay_group(z, games, dev)
+    assert total == len(z["actions"])
+
+
+def test_golden_full_observations(traces):
+    """Raw observation tensors (not only digests) at the sampled plies."""
+    from shogidrl_b200 import VecShogiEnv
+
+    z = traces
+    dev = torch.device("cuda:0")
+    idx = z["full_obs_idx"]
+    starts = np.concatenate([[0], np.cumsum(z["T"])])
+    game_of = np.searchsorted(starts, idx, side="right") - 1
+    n = len(idx)
+    mm = z["max_moves"][game_of]
+    env = VecShogiEnv(n, max_moves_per_game=500, device=dev, auto_reset=False)
+    env.load_positions(z["boards"][idx], z["hands"][idx], z["sides"][idx], z["move_counts"][idx], mm,
+                       eval_termination=False)
+    torch.cuda.synchronize()
+    assert np.array_equal(env.obs.cpu().numpy(), z["full_obs"])
+
+
+def test_kat_positions(golden_dir):
+    """Known-answer SFEN positions of the reference's test-suite (+ pins, uchifuzume, oddities)."""
+    from shogidrl_b200 import VecShogiEnv
+
+    with np.load(os.path.join(golden_dir, "kat_positions.npz")) as zf:
+        z = {k: zf[k] for k in zf.files}
+    dev = torch.device("cuda:0")
+    n = len(z["sfens"])
+    parsed = [orc.parse_sfen(str(s)) for s in z["sfens"]]
+    env = VecShogiEnv(n, max_moves_per_game=500, device=dev, auto_reset=False)
+    env.load_positions(np.stack([p[0] for p in parsed]), np.stack([p[1] for p in parsed]),
+                       np.asarray([p[2] for p in parsed]), np.asarray([p[3] for p in parsed]))
+    torch.cuda.synchronize()
+    b, h, m = [x.cpu().numpy() for x in env.export()]
+    mask = env.mask.cpu().numpy()
+    obs = env.obs.cpu().numpy()
+    for i, sfen in enumerate(z["sfens"]):
+        want = z["legal"][z["legal_off"][i]:z["legal_off"][i + 1]].astype(np.int64)
+        got = np.nonzero(mask[i])[0]
+        assert np.array_equal(got, want), (str(sfen), _explain(b[i], h[i], m[i, 0], got, want))
+        assert (m[i, 3] != 0) == bool(z["game_over"][i]), sfen
+        assert m[i, 3] == z["reason"][i] and m[i, 4] == z["winner"][i], sfen
+        assert np.array_equal(obs[i], z["obs"][i]), sfen
+
+
+def test_scripted_sennichite(golden_dir):
+    from shogidrl_b200 import VecShogiEnv
+
+    with np.load(os.path.join(golden_dir, "scripted.npz")) as zf:
+        z = {k: zf[k] for k in zf.files}
+    dev = torch.device("cuda:0")
+    env = VecShogiEnv(2, max_moves_per_game=500, device=dev, auto_reset=False)
+    p = orc.parse_sfen(str(z["senn_sfen"]))
+    start = orc.OracleGame().export()
+    env.load_positions(np.stack([p[0], start[0]]), np.stack([p[1], start[1]]), np.asarray([p[2], 0]),
+                       np.asarray([p[3], 0]))
+    a0, a1 = z["senn_actions"], z["senn2_actions"]
+    for t in range(max(len(a0), len(a1))):
+        acts = torch.tensor([int(a0[min(t, len(a0) - 1)]), int(a1[min(t, len(a1) - 1)])], device=dev)
+        out = env.step(acts)
+        if t < len(a0):
+            assert int(out["done"][0]) == int(z["senn_dones"][t]) and int(out["reason"][0]) == int(z["senn_reasons"][t]), t
+        if t < len(a1):
+            assert int(out["done"][1]) == int(z["senn2_dones"][t]) and int(out["reason"][1]) == int(z["senn2_reasons"][t]), t
+    assert int(z["senn_reasons"][-1]) == 4 and len(a0) == 13
+
+
+@pytest.mark.parametrize("n,T,max_moves", [(1024, 160, 500), (512, 120, 40)])
+def test_selfplay_vs_oracle(n, T, max_moves):
+    """Device self-play with the fused uniform-random legal action and auto-reset, against the C oracle
+    playing the same counter-based RNG: actions, rewards, dones, reasons, legal counts every step, and
+    the final boards / hands / masks / observations."""
+    from shogidrl_b200 import VecShogiEnv
+
+    dev = torch.device("cuda:0")
+    seed = 4321
+    env = VecShogiEnv(n, max_moves_per_game=max_moves, device=dev, seed=seed, auto_reset=True)
+    env.refresh(random_actions=True)
+    acts, rews, dones, reasons, counts = [], [], [], [], []
+    for t in range(T):
+        a = env.next_actions.clone()
+        counts.append(env.legal_count.clone())
+        out = env.step(a, random_actions=True)
+        acts.append(a); rews.append(out["reward"].clone()); dones.append(out["done"].clone())
+        reasons.append(out["reason"].clone())
+    torch.cuda.synchronize()
+    assert int(env.errors().abs().sum()) == 0
+    ref = orc.selfplay(n, T, max_moves=max_moves, seed=seed, threads=os.cpu_count() or 1)
+    got_a = torch.stack(acts).cpu().numpy()
+    bad = np.argwhere(got_a != ref["actions"])
+    assert len(bad) == 0, ("first action mismatch (t, env):", bad[:5], got_a[tuple(bad[0])], ref["actions"][tuple(bad[0])])
+    assert np.array_equal(torch.stack(counts).cpu().numpy(), ref["legal_counts"])
+    assert np.array_equal(torch.stack(rews).cpu().numpy(), ref["rewards"])
+    assert np.array_equal(torch.stack(dones).cpu().numpy(), ref["dones"])
+    assert np.array_equal(torch.stack(reasons).cpu().numpy(), ref["reasons"])
+    b, h, m = [x.cpu().numpy() for x in env.export()]
+    assert np.array_equal(b, ref["boards"]) and np.array_equal(h, ref["hands"])
+    assert np.array_equal(m[:, :2], ref["meta"][:, :2])
+    assert np.array_equal(env.mask.cpu().numpy(), ref["mask"])
+    assert np.array_equal(env.obs.cpu().numpy(), ref["obs"])
+    assert ref["dones"].sum() > 0  # the run crossed episode boundaries
+
+
+def test_mask_layouts_agree():
+    """Vectorised (16-byte rows) and byte-granular (contiguous 13,527-byte rows) mask writers agree, as do
+    observation rows at both 16-byte phases."""
+    from shogidrl_b200 import VecShogiEnv
+
+    dev = torch.device("cuda:0")
+    env = VecShogiEnv(64, device=dev, seed=7)
+    env.refresh(random_actions=True)
+    for _ in range(40):
+        env.step(env.next_actions.clone(), random_actions=True)
+    contiguous = torch.zeros((64, 13527), dtype=torch.uint8, device=dev)
+    obs2 = torch.zeros((64, 46, 9, 9), dtype=torch.float32, device=dev)
+    env.refresh(obs=obs2, mask=contiguous)
+    padded, obs1 = env.mask.clone(), env.obs.clone()
+    env.refresh()
+    assert torch.equal(contiguous, env.mask) and torch.equal(padded, env.mask)
+    assert torch.equal(obs2, env.obs) and torch.equal(obs1, env.obs)
+    assert torch.equal(env.mask.sum(1).int(), env.legal_count)
+
+
+def test_illegal_actions_set_error_bits():
+    from shogidrl_b200 import VecShogiEnv
+
+    dev = torch.device("cuda:0")
+    env = VecShogiEnv(4, device=dev, auto_reset=False)
+    b0, h0, m0 = [x.clone() for x in env.export()]
+    # out of range / empty source square / illegal pattern (pawn two squares) / drop without a piece in hand
+    a = torch.tensor([20000, ((40 * 80 + 30) * 2), ((54 * 80 + 36) * 2), 12960 + 40 * 7], device=dev)
+    out = env.step(a)
+    err = env.errors().cpu().numpy()
+    assert list(err) == [1, 1, 2, 1]
+    b1, h1, m1 = env.export()
+    assert torch.equal(b0, b1) and torch.equal(h0, h1) and torch.equal(m0[:, :5], m1[:, :5])
+    assert int(out["done"].sum()) == 0 and float(out["reward"].abs().sum()) == 0.0
