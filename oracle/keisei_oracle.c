@@ -584,6 +584,73 @@ long orc_selfplay(int n_envs, int env0, int T, int step0, int max_moves, uint64_
   return j.total;
 }
 
+/* Persistent batch of games for stepwise timing (bench.py --impl reference / cpu_baseline):
+ * orc_batch_run advances every game of the batch by T plies with the same per-ply work as
+ * orc_selfplay (legal moves -> mask -> make_move -> observation -> reset on done). */
+typedef struct {
+  int n, max_moves;
+  orc_game **games;
+} orc_batch;
+
+orc_batch *orc_batch_new(int n, int max_moves) {
+  orc_batch *b = (orc_batch *)calloc(1, sizeof(orc_batch));
+  b->n = n; b->max_moves = max_moves;
+  b->games = (orc_game **)calloc((size_t)n, sizeof(orc_game *));
+  for (int i = 0; i < n; i++) { b->games[i] = orc_new(); orc_reset(b->games[i], max_moves); }
+  return b;
+}
+void orc_batch_free(orc_batch *b) {
+  if (!b) return;
+  for (int i = 0; i < b->n; i++) orc_free(b->games[i]);
+  free(b->games); free(b);
+}
+typedef struct {
+  orc_batch *b; int T, step0, env0; uint64_t seed; int next_env; long total; long ply_sum; pthread_mutex_t mu;
+} bt_job;
+static void *bt_worker(void *arg) {
+  bt_job *j = (bt_job *)arg;
+  float *obs = (float *)malloc(sizeof(float) * 46 * NSQ);
+  uint8_t *mask = (uint8_t *)malloc(NACT);
+  uint16_t tmp[1024];
+  long mine = 0, plies = 0;
+  for (;;) {
+    pthread_mutex_lock(&j->mu);
+    int e = j->next_env++;
+    pthread_mutex_unlock(&j->mu);
+    if (e >= j->b->n) break;
+    orc_game *g = j->b->games[e];
+    for (int t = 0; t < j->T; t++) {
+      int n = gen_legal(g, 0, tmp);
+      memset(mask, 0, NACT);
+      for (int i = 0; i < n; i++) mask[tmp[i]] = 1;
+      qsort(tmp, n, sizeof(uint16_t), cmp_u16);
+      uint32_t r = orc_rand32(j->seed, (uint64_t)(j->env0 + e), (uint64_t)(j->step0 + t));
+      float o4[4];
+      plies += g->move_count;
+      orc_make_move(g, tmp[((uint64_t)r * (uint64_t)n) >> 32], o4);
+      orc_observation(g, obs);
+      if (g->game_over) orc_reset(g, j->b->max_moves);
+      mine++;
+    }
+  }
+  free(obs); free(mask);
+  pthread_mutex_lock(&j->mu);
+  j->total += mine; j->ply_sum += plies;
+  pthread_mutex_unlock(&j->mu);
+  return NULL;
+}
+/* returns env steps executed; *mean_ply (optional) = mean move_count of the positions stepped from */
+long orc_batch_run(orc_batch *b, int T, int step0, int env0, uint64_t seed, int n_threads, double *mean_ply) {
+  bt_job j = {b, T, step0, env0, seed, 0, 0, 0, PTHREAD_MUTEX_INITIALIZER};
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > 256) n_threads = 256;
+  pthread_t th[256];
+  for (int i = 0; i < n_threads; i++) pthread_create(&th[i], NULL, bt_worker, &j);
+  for (int i = 0; i < n_threads; i++) pthread_join(th[i], NULL);
+  if (mean_ply) *mean_ply = j.total ? (double)j.ply_sum / (double)j.total : 0.0;
+  return j.total;
+}
+
 /* ExperienceBuffer.compute_advantages_and_returns: keisei/core/experience_buffer.py:99-145,
  * column-wise over a [T, N] layout (N = 1 is the reference's flat buffer).  Every fp32
  * operation is rounded separately, in the reference's order (build with -ffp-contract=off):

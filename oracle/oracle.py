@@ -64,6 +64,11 @@ def lib() -> C.CDLL:
         L.orc_pick_action.restype = i32
         L.orc_selfplay.argtypes = [i32, i32, i32, i32, i32, u64] + [vp] * 10 + [i32]
         L.orc_selfplay.restype = C.c_long
+        L.orc_batch_new.argtypes = [i32, i32]
+        L.orc_batch_new.restype = vp
+        L.orc_batch_free.argtypes = [vp]
+        L.orc_batch_run.argtypes = [vp, i32, i32, i32, u64, i32, C.POINTER(C.c_double)]
+        L.orc_batch_run.restype = C.c_long
         L.orc_gae.argtypes = [vp, vp, vp, vp, i32, i32, C.c_double, C.c_double, vp, vp]
         _lib = L
     return _lib
@@ -213,6 +218,29 @@ def selfplay(n_envs: int, T: int, *, env0: int = 0, step0: int = 0, max_moves: i
                            _p(g("mask")), _p(g("boards")), _p(g("hands")), _p(g("meta")), threads)
     out["total_steps"] = int(total)
     return out
+
+
+class OracleBatch:
+    """Persistent batch of oracle games advanced stepwise (CPU baseline / reference arm timing)."""
+
+    def __init__(self, n: int, max_moves: int = 500, seed: int = 1234, threads: int = 1, env0: int = 0):
+        self._L = lib()
+        self._b = C.c_void_p(self._L.orc_batch_new(n, max_moves))
+        self.n, self.seed, self.threads, self.env0, self.step = n, seed, threads, env0, 0
+        self.mean_ply = 0.0
+
+    def run(self, T: int) -> int:
+        mp = C.c_double()
+        done = self._L.orc_batch_run(self._b, T, self.step, self.env0, self.seed, self.threads, C.byref(mp))
+        self.step += T
+        self.mean_ply = mp.value
+        return int(done)
+
+    def __del__(self):
+        try:
+            self._L.orc_batch_free(self._b)
+        except Exception:
+            pass
 
 
 def gae(rewards: np.ndarray, values: np.ndarray, dones: np.ndarray, last_value: np.ndarray,

@@ -1,0 +1,50 @@
+"""Device-side agent/buffer primitives: masked categorical sampling and GAE (C ABI: kz_sample_masked, kz_gae)."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native as nv
+
+
+def sample_masked(logits: torch.Tensor, mask: torch.Tensor, seed: int = 0, offset: int = 0,
+                  deterministic: bool = False, want_entropy: bool = False
+                  ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+    """Masked softmax -> Categorical sample (argmax if deterministic) -> log_prob, one warp per row.
+
+    Mirrors BaseActorCriticModel.get_action_and_value after forward() (base_actor_critic.py:64-116):
+    illegal logits -> -inf, softmax, NaN rows -> uniform, Categorical(probs) with its eps clamp."""
+    dev = nv.require_cuda(logits.device)
+    assert logits.dim() == 2 and logits.shape[1] == nv.NUM_ACTIONS and logits.stride(1) == 1
+    assert logits.dtype in (torch.float32, torch.bfloat16)
+    assert mask.shape == logits.shape and mask.stride(1) == 1 and mask.dtype in (torch.uint8, torch.bool)
+    n = logits.shape[0]
+    actions = torch.empty(n, dtype=torch.int64, device=dev)
+    logp = torch.empty(n, dtype=torch.float32, device=dev)
+    ent = torch.empty(n, dtype=torch.float32, device=dev) if want_entropy else None
+    nv.check(nv.lib().kz_sample_masked(logits.data_ptr(), int(logits.dtype == torch.bfloat16), logits.stride(0),
+                                       mask.data_ptr(), mask.stride(0), n, int(seed), int(offset), actions.data_ptr(), 1,
+                                       logp.data_ptr(), nv.ptr(ent), int(deterministic), nv.stream_ptr(dev)),
+             "kz_sample_masked")
+    return actions, logp, ent
+
+
+def gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, last_value: torch.Tensor,
+        gamma: float, lambda_gae: float, exact: bool = False,
+        out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[T, N] reverse-time GAE (experience_buffer.py:99-145).  gamma*lambda is multiplied in double first and
+    both factors are rounded to fp32 exactly as the reference's Python-float x tensor products are."""
+    dev = nv.require_cuda(rewards.device)
+    T, N = rewards.shape
+    r = rewards.contiguous().float()
+    v = values.contiguous().float()
+    d = dones.contiguous()
+    d = d.view(torch.uint8) if d.dtype == torch.bool else d.to(torch.uint8)
+    lv = last_value.to(device=dev, dtype=torch.float32).reshape(-1).expand(N).contiguous() if last_value.numel() == 1 \
+        else last_value.to(device=dev, dtype=torch.float32).contiguous()
+    adv, ret = out if out is not None else (torch.empty_like(r), torch.empty_like(r))
+    fn = nv.lib().kz_gae_exact if exact else nv.lib().kz_gae
+    nv.check(fn(r.data_ptr(), v.data_ptr(), d.data_ptr(), lv.data_ptr(), T, N, float(gamma),
+                float(gamma * lambda_gae), adv.data_ptr(), ret.data_ptr(), nv.stream_ptr(dev)), "kz_gae")
+    return adv, ret

@@ -79,21 +79,26 @@ class VecShogiEnv:
         return self.obs, self.mask
 
     def refresh(self, obs: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
-                eval_termination: bool = False, random_actions: bool = False):
+                eval_termination: bool = False, random_actions: bool = False,
+                next_out: Optional[torch.Tensor] = None):
         """Recompute obs / mask / legal_count (and optionally uniform-random legal actions) in place."""
         obs = self.obs if obs is None else obs
         mask = self.mask if mask is None else mask
         op, os_ = self._obs_args(obs)
         mp, ms = self._mask_args(mask)
         nv.check(self._L.kz_refresh(self.state.data_ptr(), self.n, self.hist_cap, op, os_, mp, ms,
-                                    self.legal_count.data_ptr(), self.next_actions.data_ptr() if random_actions else None,
+                                    self.legal_count.data_ptr(),
+                                    (self.next_actions if next_out is None else next_out).data_ptr() if random_actions else None,
                                     1, self.seed, self.step_index, self.env_offset, int(eval_termination), self._sp()),
                  "kz_refresh")
         return obs, mask
 
     def step(self, actions: torch.Tensor, obs: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
-             random_actions: bool = False, write_obs: bool = True, write_mask: bool = True) -> Dict[str, torch.Tensor]:
-        """make_move for every env.  ``obs`` / ``mask`` may point into a rollout buffer (e.g. obs_buf[t+1])."""
+             random_actions: bool = False, write_obs: bool = True, write_mask: bool = True,
+             next_out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """make_move for every env.  ``obs`` / ``mask`` may point into a rollout buffer (e.g. obs_buf[t+1]).
+        With ``random_actions`` the kernel also writes a uniform-random legal action for the returned state
+        into ``next_out`` (default ``self.next_actions``; must not alias ``actions``)."""
         assert actions.device == self.device and actions.dtype in (torch.int64, torch.int32) and actions.is_contiguous()
         obs = (self.obs if obs is None else obs) if write_obs else None
         mask = (self.mask if mask is None else mask) if write_mask else None
@@ -102,7 +107,10 @@ class VecShogiEnv:
         self.step_index += 1
         nxt = None
         if random_actions:
-            nxt = self.next_actions if actions.dtype == torch.int64 else self.next_actions.view(torch.int32)[: self.n]
+            nxt = self.next_actions if next_out is None else next_out
+            if actions.dtype == torch.int32 and nxt.dtype == torch.int64:
+                nxt = nxt.view(torch.int32)[: self.n]
+            assert nxt.data_ptr() != actions.data_ptr()
         nv.check(self._L.kz_step(self.state.data_ptr(), self.n, self.hist_cap, actions.data_ptr(),
                                  int(actions.dtype == torch.int64), op, os_, mp, ms, self.reward.data_ptr(),
                                  self.done.data_ptr(), self.reason.data_ptr(), self.winner.data_ptr(),
