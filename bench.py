@@ -101,7 +101,7 @@ class ClockSampler:
 def cpu_baseline_sample(threads: int, seconds_budget: float = 20.0):
     """The oracle port timed on the host cores on a bounded sample of the same workload."""
     from oracle import oracle as orc
-    n = 32 * threads
+    n = 256 * threads
     batch = orc.OracleBatch(n, MAX_MOVES, SEED, threads)
     batch.run(8)  # warm caches / threads
     t0 = time.perf_counter()

@@ -1,0 +1,60 @@
+"""CPU-only checks of the C-ABI library: it loads without a GPU and exports every symbol that
+include/keisei_b200.h declares (no compute calls here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from shogidrl_b200 import _native as nv
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "keisei_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(kz_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    L = nv.lib()
+    names = _declared()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/keisei_b200.h but not exported"
+    assert sorted(nv.EXPORTS) == names
+
+
+def test_abi_version_and_layout():
+    L = nv.lib()
+    assert L.kz_abi_version() == 1
+    offs = (C.c_int64 * 3)()
+    total = C.c_int64()
+    assert L.kz_state_layout(65536, 500, offs, C.byref(total)) == 0
+    assert offs[0] == 0 and offs[1] == 65536 * 96 and offs[2] % 256 == 0
+    # boards + meta + 500 plies x 16-byte keys (split by parity, padded): ~8.1 kB per game
+    per_game = total.value / 65536
+    assert 96 + 32 + 500 * 16 <= per_game <= 96 + 32 + 512 * 16 + 1
+    assert L.kz_state_layout(0, 500, offs, C.byref(total)) == -1  # KZ_E_ARG
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from shogidrl_b200 import VecShogiEnv, NativeError
+    with pytest.raises(NativeError):
+        VecShogiEnv(4)
+    with pytest.raises(NativeError):
+        VecShogiEnv(4, device="cpu")
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under shogidrl_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "shogidrl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower() or f == "_never_", (dirpath, f)

@@ -1,0 +1,131 @@
+"""GPU tests of kz_sample_masked and kz_gae through the C ABI (shogidrl_b200.rl)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as orc  # noqa: E402  (checker only)
+
+A = 13527
+
+
+def _torch_reference(logits, mask):
+    """base_actor_critic.py:64-116 in plain fp32 torch."""
+    masked = torch.where(mask.bool(), logits.float(), torch.tensor(float("-inf"), device=logits.device))
+    probs = torch.softmax(masked, dim=-1)
+    nan_rows = torch.isnan(probs).any(dim=1)
+    probs[nan_rows] = 1.0 / A
+    return probs, torch.distributions.Categorical(probs=probs)
+
+
+def _random_case(n, dev, seed=0, legal_p=0.004):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    logits = (torch.randn(n, A, generator=g) * 3).to(dev)
+    mask = (torch.rand(n, A, generator=g) < legal_p).to(dev)
+    mask[:, 17] |= ~mask.any(dim=1)
+    return logits, mask
+
+
+def test_sample_support_and_logprob():
+    from shogidrl_b200 import rl
+    dev = torch.device("cuda:0")
+    logits, mask = _random_case(512, dev)
+    act, logp, ent = rl.sample_masked(logits, mask, seed=3, offset=11, want_entropy=True)
+    assert bool(mask.gather(1, act[:, None]).all())
+    probs, dist = _torch_reference(logits, mask)
+    ref_lp = dist.log_prob(act)
+    # fp32 softmax; tolerance 1e-5 relative (+1e-6 absolute) on log-probabilities and entropy
+    assert torch.allclose(logp, ref_lp, rtol=1e-5, atol=1e-6), float((logp - ref_lp).abs().max())
+    assert torch.allclose(ent, dist.entropy(), rtol=1e-5, atol=1e-5), float((ent - dist.entropy()).abs().max())
+
+
+def test_sample_deterministic_is_argmax():
+    from shogidrl_b200 import rl
+    dev = torch.device("cuda:0")
+    logits, mask = _random_case(256, dev, seed=1)
+    act, logp, _ = rl.sample_masked(logits, mask, deterministic=True)
+    probs, dist = _torch_reference(logits, mask)
+    assert torch.equal(act, torch.argmax(probs, dim=-1))
+    assert torch.allclose(logp, dist.log_prob(act), rtol=1e-5, atol=1e-6)
+
+
+def test_sample_single_legal_and_all_illegal():
+    from shogidrl_b200 import rl
+    dev = torch.device("cuda:0")
+    logits = torch.randn(4, A, device=dev)
+    mask = torch.zeros(4, A, dtype=torch.bool, device=dev)
+    mask[0, 5] = True
+    mask[1, A - 1] = True
+    act, logp, _ = rl.sample_masked(logits, mask, seed=9)
+    assert int(act[0]) == 5 and int(act[1]) == A - 1
+    eps = torch.finfo(torch.float32).eps
+    assert abs(float(logp[0]) - float(np.log(np.float32(1.0) - np.float32(eps)))) < 1e-9
+    # all-illegal rows: uniform over all actions (base_actor_critic.py:93-101)
+    assert 0 <= int(act[2]) < A and abs(float(logp[2]) - float(np.log(1.0 / A))) < 1e-5
+
+
+def test_sample_bf16_and_strided_mask():
+    from shogidrl_b200 import rl
+    dev = torch.device("cuda:0")
+    logits, mask = _random_case(128, dev, seed=2)
+    lb = logits.to(torch.bfloat16)
+    store = torch.zeros(128, 13536, dtype=torch.uint8, device=dev)
+    store[:, :A] = mask
+    act, logp, _ = rl.sample_masked(lb, store[:, :A], seed=5)
+    assert bool(mask.gather(1, act[:, None]).all())
+    _, dist = _torch_reference(lb.float(), mask)
+    assert torch.allclose(logp, dist.log_prob(act), rtol=1e-5, atol=1e-6)
+
+
+def test_sample_frequencies_chi2():
+    """Statistical parity with the masked softmax: chi-square on 160k draws over 12 legal actions."""
+    from shogidrl_b200 import rl
+    dev = torch.device("cuda:0")
+    legal = torch.tensor([3, 40, 41, 999, 5000, 5001, 8191, 8192, 12959, 12960, 13000, 13526], device=dev)
+    row = torch.randn(A, device=dev)
+    row[legal] = torch.linspace(-1.5, 2.0, len(legal), device=dev)
+    n = 16000
+    logits = row[None].expand(n, A).contiguous()
+    mask = torch.zeros(n, A, dtype=torch.bool, device=dev)
+    mask[:, legal] = True
+    counts = torch.zeros(A, device=dev)
+    for rep in range(10):
+        act, _, _ = rl.sample_masked(logits, mask, seed=77, offset=rep * n)
+        counts += torch.bincount(act, minlength=A).float()
+    assert float(counts.sum()) == 10 * n and float(counts[legal].sum()) == 10 * n
+    p = torch.softmax(row[legal], 0)
+    expected = p * 10 * n
+    chi2 = float((((counts[legal] - expected) ** 2) / expected).sum())
+    assert chi2 < 40.0, chi2  # 11 dof: P(chi2 > 40) ~ 4e-5
+
+
+def test_gae_golden_and_oracle(golden_dir):
+    from shogidrl_b200 import rl
+    dev = torch.device("cuda:0")
+    with np.load(os.path.join(golden_dir, "gae_golden.npz")) as zf:
+        z = {k: zf[k] for k in zf.files}
+    for i in range(int(z["n_cases"])):
+        r = torch.as_tensor(z[f"c{i}_r"][:, None]).to(dev)
+        v = torch.as_tensor(z[f"c{i}_v"][:, None]).to(dev)
+        d = torch.as_tensor(z[f"c{i}_d"][:, None]).to(dev)
+        lv = torch.tensor([float(z[f"c{i}_last"])], device=dev)
+        gamma, lam = float(z[f"c{i}_gamma"]), float(z[f"c{i}_lam"])
+        adv, ret = rl.gae(r, v, d, lv, gamma, lam, exact=True)  # column kernel: bit-exact with the reference
+        assert np.array_equal(adv[:, 0].cpu().numpy(), z[f"c{i}_adv"]), i
+        assert np.array_equal(ret[:, 0].cpu().numpy(), z[f"c{i}_ret"]), i
+        adv2, ret2 = rl.gae(r, v, d, lv, gamma, lam)             # narrow -> warp-scan kernel: 1e-5 relative
+        scale = max(1.0, float(np.abs(z[f"c{i}_adv"]).max()))
+        assert float((adv2[:, 0].cpu() - torch.as_tensor(z[f"c{i}_adv"])).abs().max()) <= 1e-5 * scale, i
+        assert float((ret2[:, 0].cpu() - torch.as_tensor(z[f"c{i}_ret"])).abs().max()) <= 1e-5 * scale, i
+    # wide rollout: [T=128, N=4096] against the oracle, bit-exact
+    g = torch.Generator(device="cpu").manual_seed(5)
+    T, N = 128, 4096
+    r = torch.randn(T, N, generator=g); v = torch.randn(T, N, generator=g)
+    d = torch.rand(T, N, generator=g) < 0.03
+    lv = torch.randn(N, generator=g)
+    adv, ret = rl.gae(r.to(dev), v.to(dev), d.to(dev), lv.to(dev), 0.99, 0.95)
+    a_ref, r_ref = orc.gae(r.numpy(), v.numpy(), d.numpy(), lv.numpy(), 0.99, 0.95)
+    assert np.array_equal(adv.cpu().numpy(), a_ref) and np.array_equal(ret.cpu().numpy(), r_ref)
