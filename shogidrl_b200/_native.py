@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkeisei_b200.so")
+LIB_PATH = os.environ.get("KZ_LIB_PATH") or os.path.join(_HERE, "libkeisei_b200.so")  # override: kernel tuning only
 
 NUM_ACTIONS = 13527
 OBS_FLOATS = 46 * 81

@@ -7,8 +7,18 @@
 
 #define FULL 0xffffffffu
 #define BITMAP_WORDS 424      // ceil(13527 / 32) = 423, padded to a multiple of 4
+#ifndef WARPS_PER_CTA
 #define WARPS_PER_CTA 8
+#endif
+#ifndef MIN_CTAS_PER_SM
+#define MIN_CTAS_PER_SM 2
+#endif
+#ifndef SYNC_MODE
+#define SYNC_MODE 0
+#endif
+#ifndef CTAS_PER_SM
 #define CTAS_PER_SM 4
+#endif
 
 // step-target classes of the STEP table
 #define CLS_BP 0

@@ -38,17 +38,20 @@ struct __align__(16) WarpScratch {
   uint8_t dropv[96];      // 7 drop bits per square
 };
 
-struct Tables {
-  const uint32_t* ray;
-  const uint32_t* step;
-};
+// Shared memory of the step kernel, declared at file scope so that every device function addresses it
+// with shared-space loads/stores (LDS/STS) instead of generic ones.
+__shared__ uint32_t s_ray[81 * 8 * 3];
+__shared__ uint32_t s_step[NCLS * 81 * 3];
+__shared__ WarpScratch s_ws[WARPS_PER_CTA];
 
-__device__ __forceinline__ BB ld_ray(const Tables& T, int sq, int d) {
-  const uint32_t* p = T.ray + (sq * 8 + d) * 3;
+struct Tables {};  // the tables live in s_ray / s_step
+
+__device__ __forceinline__ BB ld_ray(const Tables&, int sq, int d) {
+  const uint32_t* p = s_ray + (sq * 8 + d) * 3;
   return BB{p[0], p[1], p[2]};
 }
-__device__ __forceinline__ BB ld_step(const Tables& T, int cls, int sq) {
-  const uint32_t* p = T.step + (cls * 81 + sq) * 3;
+__device__ __forceinline__ BB ld_step(const Tables&, int cls, int sq) {
+  const uint32_t* p = s_step + (cls * 81 + sq) * 3;
   return BB{p[0], p[1], p[2]};
 }
 
@@ -76,15 +79,16 @@ struct GenResult {
 // for uchifuzume instead of only the square in front of the enemy king (needed only for loaded
 // positions in which the side NOT to move is already in check).
 template <bool EMIT>
-__device__ __noinline__ GenResult gen_moves(WarpScratch& ws, const Tables& T, const uint32_t tab, const int lane,
-                                            const int me, const uint8_t* hands, const bool skip_ufz,
-                                            const bool ufz_all);
+__device__ __noinline__ GenResult gen_moves(const uint32_t tab, const int me, const bool skip_ufz, const bool ufz_all);
 
 template <bool EMIT>
-__device__ __forceinline__ GenResult gen_moves_impl(WarpScratch& ws, const Tables& T, const uint32_t tab,
-                                                    const int lane, const int me, const uint8_t* hands,
-                                                    const bool skip_ufz, const bool ufz_all) {
+__device__ __forceinline__ GenResult gen_moves_impl(const uint32_t tab, const int me, const bool skip_ufz,
+                                                    const bool ufz_all) {
   constexpr int SCR = EMIT ? 0 : 1;  // scratch set: the count-only instance runs inside the emitting one
+  const int lane = threadIdx.x & 31;
+  WarpScratch& ws = s_ws[threadIdx.x >> 5];
+  const uint8_t* hands = ws.meta;
+  const Tables T{};
   GenResult res;
   res.count = 0;
   res.in_check = false;
@@ -246,7 +250,7 @@ __device__ __forceinline__ GenResult gen_moves_impl(WarpScratch& ws, const Table
       __syncwarp();
       if (lane == 0) ws.board[D] = (uint8_t)pcode;
       __syncwarp();
-      GenResult sub = gen_moves<false>(ws, T, tab, lane, 1 - me, hands, true, false);
+      GenResult sub = gen_moves<false>(tab, 1 - me, true, false);
       __syncwarp();
       if (lane == 0) ws.board[D] = 0;
       __syncwarp();
@@ -371,10 +375,8 @@ __device__ __forceinline__ GenResult gen_moves_impl(WarpScratch& ws, const Table
 }
 
 template <bool EMIT>
-__device__ __noinline__ GenResult gen_moves(WarpScratch& ws, const Tables& T, const uint32_t tab, const int lane,
-                                            const int me, const uint8_t* hands, const bool skip_ufz,
-                                            const bool ufz_all) {
-  return gen_moves_impl<EMIT>(ws, T, tab, lane, me, hands, skip_ufz, ufz_all);
+__device__ __noinline__ GenResult gen_moves(const uint32_t tab, const int me, const bool skip_ufz, const bool ufz_all) {
+  return gen_moves_impl<EMIT>(tab, me, skip_ufz, ufz_all);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -415,8 +417,8 @@ __device__ __forceinline__ uint4 position_key(const WarpScratch& ws, int lane, i
 struct StepParams {
   uint8_t* boards;
   uint8_t* meta;
-  uint4* hist;
-  int hist_half;  // entries per parity array
+  uint4* hist;    // repetition tables: rep_slots 16-byte slots per game
+  int rep_slots;  // power of two >= 2 * hist_cap (>= 64)
   int hist_cap;
   int n;
   const void* actions;
@@ -452,26 +454,39 @@ __device__ __forceinline__ uint32_t rand32(unsigned long long seed, unsigned lon
 __device__ __forceinline__ uint16_t ld_u16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
 __device__ __forceinline__ void st_u16(uint8_t* p, int v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) kz_step_kernel(const StepParams P) {
-  __shared__ uint32_t s_ray[81 * 8 * 3];
-  __shared__ uint32_t s_step[NCLS * 81 * 3];
-  __shared__ WarpScratch s_ws[WARPS_PER_CTA];
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_kernel(const StepParams P) {
   for (int i = threadIdx.x; i < 81 * 8 * 3; i += blockDim.x) s_ray[i] = g_ray[i];
   for (int i = threadIdx.x; i < NCLS * 81 * 3; i += blockDim.x) s_step[i] = g_step[i];
   __syncthreads();
-  const Tables T{s_ray, s_step};
+  const Tables T{};
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpScratch& ws = s_ws[warp];
   const uint32_t tab = code_info(lane);
 
-  for (int g = blockIdx.x * WARPS_PER_CTA + warp; g < P.n; g += gridDim.x * WARPS_PER_CTA) {
-    // ---- load state
-    {
-      const uint32_t* bsrc = reinterpret_cast<const uint32_t*>(P.boards + (size_t)g * 96);
-      const uint32_t* msrc = reinterpret_cast<const uint32_t*>(P.meta + (size_t)g * 32);
-      if (lane < 24) reinterpret_cast<uint32_t*>(ws.board)[lane] = bsrc[lane];
-      else reinterpret_cast<uint32_t*>(ws.meta)[lane - 24] = msrc[lane - 24];
-    }
+  // One 32-bit word of game state per lane (lanes 0-23: board, 24-31: meta) and the action are fetched one
+  // game ahead, so that their DRAM latency overlaps the previous game's work.
+  auto fetch_state = [&](int g) -> uint32_t {
+    if (g >= P.n) return 0u;
+    return lane < 24 ? reinterpret_cast<const uint32_t*>(P.boards + (size_t)g * 96)[lane]
+                     : reinterpret_cast<const uint32_t*>(P.meta + (size_t)g * 32)[lane - 24];
+  };
+  auto fetch_action = [&](int g) -> long long {
+    if (g >= P.n || P.mode != 1) return 0;
+    return P.actions_i64 ? reinterpret_cast<const long long*>(P.actions)[g]
+                         : (long long)reinterpret_cast<const int*>(P.actions)[g];
+  };
+  const int g_first = blockIdx.x * WARPS_PER_CTA + warp, g_stride = gridDim.x * WARPS_PER_CTA;
+  uint32_t next_word = fetch_state(g_first);
+  long long next_action = fetch_action(g_first);
+
+  for (int g = g_first; g < P.n; g += g_stride) {
+    // ---- state of this game (prefetched), start fetching the next one
+    __syncwarp();
+    if (lane < 24) reinterpret_cast<uint32_t*>(ws.board)[lane] = next_word;
+    else reinterpret_cast<uint32_t*>(ws.meta)[lane - 24] = next_word;
+    const long long a = next_action;
+    next_word = fetch_state(g + g_stride);
+    next_action = fetch_action(g + g_stride);
     __syncwarp();
     int side = ws.meta[14];
     int status = ws.meta[15];
@@ -489,8 +504,6 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) kz_step_kernel(const StepP
     bool moved = false;
 
     if (P.mode == 1) {
-      long long a = P.actions_i64 ? reinterpret_cast<const long long*>(P.actions)[g]
-                                  : (long long)reinterpret_cast<const int*>(P.actions)[g];
       if (status != 0) {
         // make_move on a finished game returns the terminal tuple again (shogi_game.py:589-593)
       } else if (a < 0 || a >= KZ_NUM_ACTIONS) {
@@ -549,18 +562,33 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) kz_step_kernel(const StepP
           move_count += 1;  // apply_move_to_game (shogi_move_execution.py:141-156)
           side = 1 - side;
           // history append + repetition count (shogi_game.py:651-654, shogi_rules_logic.py:680-695)
+          // The reference counts equal (board, hands, side) entries of move_history; here every game owns an
+          // open-addressing table keyed by the 124-bit position key whose low 4 bits of w hold the occurrence
+          // count.  One cooperative probe reads 32 consecutive slots (512 B) instead of scanning every earlier ply.
           const uint4 key = position_key(ws, lane, side);
           if (hist_len < P.hist_cap) {
-            uint4* hp = P.hist + ((size_t)g * 2 + (hist_len & 1)) * P.hist_half;
-            const int nprev = hist_len >> 1;
-            int matches = 0;
-            for (int i = lane; i < nprev; i += 32) {
-              const uint4 e = hp[i];
-              matches += (e.x == key.x && e.y == key.y && e.z == key.z && e.w == key.w);
+            uint4* tb = P.hist + (size_t)g * P.rep_slots;
+            const uint32_t smask = (uint32_t)P.rep_slots - 1u;
+            uint32_t start = key.y & smask;
+            int count = 0;
+            for (int round = 0; round * 32 < P.rep_slots; round++) {
+              const uint32_t slot = (start + lane) & smask;
+              const uint4 e = tb[slot];
+              const bool occupied = (e.w & 15u) != 0;
+              const bool match = occupied && e.x == key.x && e.y == key.y && e.z == key.z && ((e.w ^ key.w) >> 4) == 0;
+              const uint32_t stop = __ballot_sync(FULL, match || !occupied);
+              if (stop) {
+                const int f = __ffs(stop) - 1;
+                const uint32_t oldw = __shfl_sync(FULL, e.w, f);
+                const bool was_match = (__ballot_sync(FULL, match) >> f) & 1;
+                count = was_match ? min(15, (int)(oldw & 15u) + 1) : 1;
+                if (lane == f) tb[slot] = make_uint4(key.x, key.y, key.z, (key.w & ~15u) | (uint32_t)count);
+                break;
+              }
+              start += 32;
             }
-            matches = __reduce_add_sync(FULL, matches);
-            if (lane == 0) hp[nprev] = key;
-            fresh_senn = matches + 1 >= 4;
+            if (count == 0) err |= KZ_ERR_HISTORY_FULL;
+            fresh_senn = count >= 4;
             hist_len += 1;
           } else {
             err |= KZ_ERR_HISTORY_FULL;
@@ -571,11 +599,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) kz_step_kernel(const StepP
 
     // ---- legal moves of the position now on the board
     const bool ufz_all = (P.mode == 0);  // loaded positions may have the side not to move in check
-    GenResult gr = gen_moves<true>(ws, T, tab, lane, side, ws.meta, false, false);
+    GenResult gr = gen_moves<true>(tab, side, false, false);
     if (ufz_all) {
       // anomaly test: only when the opponent's king is attacked can a pawn drop elsewhere "give check"
-      GenResult opp = gen_moves<false>(ws, T, tab, lane, 1 - side, ws.meta, true, false);
-      if (opp.in_check && ws.meta[side * 7] > 0) gr = gen_moves<true>(ws, T, tab, lane, side, ws.meta, false, true);
+      GenResult opp = gen_moves<false>(tab, 1 - side, true, false);
+      if (opp.in_check && ws.meta[side * 7] > 0) gr = gen_moves<true>(tab, side, false, true);
     }
 
     if ((moved || (P.mode == 0 && P.eval_term)) && status == 0) {
@@ -601,6 +629,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) kz_step_kernel(const StepP
       if (lane < 14) ws.meta[lane] = 0;
       side = 0; status = 0; winner = -1; move_count = 0; hist_len = 0;
       episodes += 1;
+      {
+        uint4* tb = P.hist + (size_t)g * P.rep_slots;
+        for (int i = lane; i < P.rep_slots; i += 32) tb[i] = make_uint4(0, 0, 0, 0);
+      }
       for (int i = lane; i < BITMAP_WORDS; i += 32) ws.bitmap[i] = g_init_bitmap[i];
       gr.count = 30;
       gr.in_check = false;
@@ -620,15 +652,52 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) kz_step_kernel(const StepP
     if (P.mask) {
       uint8_t* mrow = P.mask + (size_t)g * P.mask_stride;
       if (P.mask_vec) {
+        // 16-byte chunk q of the row = bits [16q, 16q+16) of the bitmap; a from-square owns chunks 10f..10f+9.
+        // Pass 1 zero-fills the 810 board-move chunks with plain 128-bit stores; pass 2 expands only the chunks
+        // of from-squares that have a legal move (3 squares x 10 chunks per warp round) and the 36 drop chunks.
         uint4* m4 = reinterpret_cast<uint4*>(mrow);
-        for (int q = lane; q < 846; q += 32) {
-          const uint32_t w = ws.bitmap[q >> 1];
-          const uint32_t b16 = (q & 1) ? (w >> 16) : (w & 0xFFFF);
+        const uint4 z4 = make_uint4(0, 0, 0, 0);
+#pragma unroll 2
+        for (int q = lane; q < 810; q += 32) m4[q] = z4;
+        uint32_t act[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const int f = lane + 32 * j;
+          bool nz = false;
+          if (f < 81) {
+            const uint32_t* w = ws.bitmap + 5 * f;
+            nz = (w[0] | w[1] | w[2] | w[3] | w[4]) != 0;
+          }
+          act[j] = __ballot_sync(FULL, nz);
+        }
+        int nact = 0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          if ((act[j] >> lane) & 1) ws.plist[0][nact + __popc(act[j] & ((1u << lane) - 1))] = (uint8_t)(lane + 32 * j);
+          nact += __popc(act[j]);
+        }
+        __syncwarp();  // orders the zero fill before the overwrites below and publishes plist
+        auto expand = [](uint32_t b16) {
           uint4 v;
           v.x = ((b16 & 0xF) * 0x00204081u) & 0x01010101u;
           v.y = (((b16 >> 4) & 0xF) * 0x00204081u) & 0x01010101u;
           v.z = (((b16 >> 8) & 0xF) * 0x00204081u) & 0x01010101u;
-          v.w = ((b16 >> 12) * 0x00204081u) & 0x01010101u;
+          v.w = (((b16 >> 12) & 0xF) * 0x00204081u) & 0x01010101u;
+          return v;
+        };
+        const int sub = lane / 10, jj = lane - 10 * sub;  // lanes 30, 31 idle in pass 2
+#pragma unroll 1
+        for (int base = 0; base < nact; base += 3) {
+          const int i = base + sub;
+          if (sub < 3 && i < nact) {
+            const int f = ws.plist[0][i];
+            const uint32_t w = ws.bitmap[5 * f + (jj >> 1)];
+            m4[10 * f + jj] = expand((jj & 1) ? (w >> 16) : (w & 0xFFFF));
+          }
+        }
+        for (int q = 810 + lane; q < 846; q += 32) {
+          const uint32_t w = ws.bitmap[q >> 1];
+          const uint4 v = expand((q & 1) ? (w >> 16) : (w & 0xFFFF));
           if (q < 845 || P.mask_stride >= 13536) m4[q] = v;
           else {  // last 7 bytes of an exactly-13,527-byte aligned row
             const uint32_t parts[2] = {v.x, v.y};
@@ -684,17 +753,25 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) kz_step_kernel(const StepP
       else if (lane == 15) pv = max_moves > 0 ? (float)((double)move_count / (double)max_moves) : 0.f;
       const int mis = ((uintptr_t)orow & 15) ? 2 : 0;  // rows are 8-byte aligned; odd rows start 8 past a 16-byte line
       float4* o4 = reinterpret_cast<float4*>(orow + mis);
-      for (int it = 0; it < 30; it++) {  // 30 x 32 chunks >= 931; uniform trip count keeps the shuffles convergent
-        const int q = it * 32 + lane;
-        const int i0 = mis + 4 * q;
-        float v[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const int x = i0 + e - 2268;
-          const int pl = x >= 0 ? ((x * 1619) >> 17) : 31;   // floor(x / 81); lane 31 holds 0
-          v[e] = __shfl_sync(FULL, pv, pl & 31);
-        }
-        if (q < 931) o4[q] = make_float4(v[0], v[1], v[2], v[3]);
+      // float4 chunk q covers floats [mis + 4q, mis + 4q + 4).  Chunks 0..565 lie inside the 28 board planes
+      // (floats < 2268): zero fill, the pieces are scattered afterwards.  Chunks 566..930 carry the constant planes.
+      const float4 zf = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+      for (int q = lane; q < 566; q += 32) o4[q] = zf;
+#pragma unroll 1
+      for (int it = 0; it < 12; it++) {  // 12 x 32 >= 365 chunks; uniform trip count keeps the shuffles convergent
+        const int q = 566 + it * 32 + lane;
+        const int x0 = mis + 4 * q - 2268;               // >= -4: index into the constant planes
+        const int xa = x0 < 0 ? 0 : x0, xb = x0 + 3;
+        const int pa = (xa * 1619) >> 17, pb = (xb * 1619) >> 17;   // floor(x / 81) for x < 1600
+        const float va = __shfl_sync(FULL, pv, pa & 31), vb = __shfl_sync(FULL, pv, pb & 31);
+        const int edge = pb * 81 - x0;                    // first float of the chunk that lies in plane pb
+        float4 v;  // floats with a negative index still belong to board plane 27 (zero here)
+        v.x = x0 < 0 ? 0.f : (0 >= edge ? vb : va);
+        v.y = x0 + 1 < 0 ? 0.f : (1 >= edge ? vb : va);
+        v.z = x0 + 2 < 0 ? 0.f : (2 >= edge ? vb : va);
+        v.w = x0 + 3 < 0 ? 0.f : vb;
+        if (q < 931) o4[q] = v;
       }
       if (lane == 0) {  // the 2 floats the float4 grid does not cover: plane 0 head or plane 45 tail, both 0 here
         float2* o2 = reinterpret_cast<float2*>(orow + (mis ? 0 : 3724));
@@ -737,11 +814,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) kz_step_kernel(const StepP
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void kz_reset_kernel(uint8_t* boards, uint8_t* meta, int n, const uint8_t* env_mask, int max_moves) {
+__global__ void kz_reset_kernel(uint8_t* boards, uint8_t* meta, uint4* rep, int rep_slots, int n,
+                                const uint8_t* env_mask, int max_moves) {
   const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (g >= n) return;
   if (env_mask && !env_mask[g]) return;
+  if (rep) for (int i = lane; i < rep_slots; i += 32) rep[(size_t)g * rep_slots + i] = make_uint4(0, 0, 0, 0);
   uint32_t* b = reinterpret_cast<uint32_t*>(boards + (size_t)g * 96);
   uint32_t* m = reinterpret_cast<uint32_t*>(meta + (size_t)g * 32);
   if (lane < 24) b[lane] = reinterpret_cast<const uint32_t*>(c_init_board)[lane];
@@ -755,11 +834,13 @@ __global__ void kz_reset_kernel(uint8_t* boards, uint8_t* meta, int n, const uin
   }
 }
 
-__global__ void kz_load_kernel(uint8_t* boards, uint8_t* meta, int n, const int8_t* src_b, const uint8_t* src_h,
-                               const uint8_t* src_side, const int32_t* src_mc, const int32_t* src_mm) {
+__global__ void kz_load_kernel(uint8_t* boards, uint8_t* meta, uint4* rep, int rep_slots, int n, const int8_t* src_b,
+                               const uint8_t* src_h, const uint8_t* src_side, const int32_t* src_mc,
+                               const int32_t* src_mm) {
   const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (g >= n) return;
+  for (int i = lane; i < rep_slots; i += 32) rep[(size_t)g * rep_slots + i] = make_uint4(0, 0, 0, 0);
   uint8_t* b = boards + (size_t)g * 96;
   uint8_t* m = meta + (size_t)g * 32;
   for (int i = lane; i < 96; i += 32) b[i] = i < 81 ? (uint8_t)src_b[(size_t)g * 81 + i] : 0;
@@ -816,15 +897,16 @@ int cuda_fail(cudaError_t e) {
 int g_sm_count = 0;
 bool g_host_ready = false;
 
-struct Layout { int64_t off_boards, off_meta, off_hist, total; int hist_half; };
+struct Layout { int64_t off_boards, off_meta, off_hist, total; int rep_slots; };
 Layout layout(int n, int hist_cap) {
   Layout L;
-  L.hist_half = ((hist_cap + 1) / 2 + 3) & ~3;
+  L.rep_slots = 64;  // power of two >= 2 * hist_cap keeps the load factor below 1/2
+  while (L.rep_slots < 2 * hist_cap) L.rep_slots *= 2;
   L.off_boards = 0;
   L.off_meta = (int64_t)n * 96;
   L.off_hist = L.off_meta + (int64_t)n * 32;
   L.off_hist = (L.off_hist + 255) & ~(int64_t)255;
-  L.total = L.off_hist + (int64_t)n * 2 * L.hist_half * 16;
+  L.total = L.off_hist + (int64_t)n * L.rep_slots * 16;
   return L;
 }
 
@@ -837,7 +919,7 @@ int launch_step(void* state, int n, int hist_cap, StepParams P, cudaStream_t st)
   P.boards = base + L.off_boards;
   P.meta = base + L.off_meta;
   P.hist = reinterpret_cast<uint4*>(base + L.off_hist);
-  P.hist_half = L.hist_half;
+  P.rep_slots = L.rep_slots;
   P.hist_cap = hist_cap;
   P.n = n;
   if (P.obs) {
@@ -935,7 +1017,7 @@ int kz_init_tables(void* stream) {
     void* scratch = nullptr;
     CK(cudaMalloc(&scratch, L.total + KZ_MASK_PAD_STRIDE));
     uint8_t* sb = reinterpret_cast<uint8_t*>(scratch);
-    kz_reset_kernel<<<1, 32, 0, st>>>(sb + L.off_boards, sb + L.off_meta, 1, nullptr, 500);
+    kz_reset_kernel<<<1, 32, 0, st>>>(sb + L.off_boards, sb + L.off_meta, nullptr, 0, 1, nullptr, 500);
     StepParams P{};
     P.mask = sb + L.total;
     P.mask_stride = KZ_MASK_PAD_STRIDE;
@@ -960,8 +1042,8 @@ int kz_reset(void* state, int n, int hist_cap, const uint8_t* env_mask, int max_
   if (!g_host_ready) return KZ_E_NOT_INIT;
   const Layout L = layout(n, hist_cap);
   uint8_t* base = reinterpret_cast<uint8_t*>(state);
-  kz_reset_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(base + L.off_boards, base + L.off_meta, n,
-                                                                                   env_mask, max_moves);
+  kz_reset_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      base + L.off_boards, base + L.off_meta, reinterpret_cast<uint4*>(base + L.off_hist), L.rep_slots, n, env_mask, max_moves);
   CK(cudaGetLastError());
   return KZ_OK;
 }
@@ -971,8 +1053,9 @@ int kz_load_positions(void* state, int n, int hist_cap, const int8_t* boards, co
   if (!state || n <= 0 || !boards || !hands || !side || !move_count || !max_moves) return KZ_E_ARG;
   const Layout L = layout(n, hist_cap);
   uint8_t* base = reinterpret_cast<uint8_t*>(state);
-  kz_load_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(base + L.off_boards, base + L.off_meta, n,
-                                                                                  boards, hands, side, move_count, max_moves);
+  kz_load_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      base + L.off_boards, base + L.off_meta, reinterpret_cast<uint4*>(base + L.off_hist), L.rep_slots, n, boards, hands, side,
+      move_count, max_moves);
   CK(cudaGetLastError());
   return KZ_OK;
 }

@@ -33,9 +33,9 @@ def test_abi_version_and_layout():
     total = C.c_int64()
     assert L.kz_state_layout(65536, 500, offs, C.byref(total)) == 0
     assert offs[0] == 0 and offs[1] == 65536 * 96 and offs[2] % 256 == 0
-    # boards + meta + 500 plies x 16-byte keys (split by parity, padded): ~8.1 kB per game
+    # boards + meta + 1024-slot repetition table of 16-byte slots: ~16.5 kB per game
     per_game = total.value / 65536
-    assert 96 + 32 + 500 * 16 <= per_game <= 96 + 32 + 512 * 16 + 1
+    assert 96 + 32 + 1024 * 16 <= per_game <= 96 + 32 + 1024 * 16 + 1
     assert L.kz_state_layout(0, 500, offs, C.byref(total)) == -1  # KZ_E_ARG
 
 
