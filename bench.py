@@ -34,7 +34,14 @@ OBS_B, MASK_B, SCALARS_B, ACTION_B, STATE_B, HIST_APPEND_B = 14904, 13527, 7, 8,
 
 
 def algorithmic_bytes_per_step(mean_ply: float) -> float:
+    """28,438 written + 8 action + 238 state + 16 history append + 8*ply history scan."""
     return OBS_B + MASK_B + SCALARS_B + ACTION_B + STATE_B + HIST_APPEND_B + 8.0 * mean_ply
+
+
+def implementation_bytes_per_step() -> float:
+    """What this implementation must move per env step: the same outputs and action, 96+32 B of state read and
+    written, and one 512 B probe + 16 B update of the repetition table (no per-ply scan)."""
+    return OBS_B + MASK_B + SCALARS_B + ACTION_B + 2 * 128 + 512 + 16
 
 
 def measured_peak_gbs():
@@ -288,7 +295,9 @@ def run_product(args):
                        "l2": "each step writes 1.86 GB of fresh obs+mask rows per GPU (2-slot ring), far above the 126 MB L2",
                        "algorithmic_bytes_per_env_step": algorithmic_bytes_per_step(mean_ply), "env_error_flags": errs},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "kz_step_kernel", "kernel_ms": kernel_ms, "peak_source": peak_src},
+                         "traffic": traffic, "kernel": "kz_step_kernel", "kernel_ms": kernel_ms, "peak_source": peak_src,
+                         "achieved_implementation_bytes": implementation_bytes_per_step() * n / (kernel_ms * 1e-3) / 1e9,
+                         "frac_implementation_bytes": implementation_bytes_per_step() * n / (kernel_ms * 1e-3) / 1e9 / peak},
             "e2e": {"value": world * n * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * n,
                     "d2h_bytes_per_step": 15 * n, "steps": e2e_steps,
                     "note": "VecShogiEnv.step with actions from pinned host memory and reward/done/reason/winner/next-action "

@@ -517,6 +517,7 @@ typedef struct {
   uint64_t seed;
   int32_t *actions; float *rewards; uint8_t *dones; uint8_t *reasons; int32_t *legal_counts;
   float *obs_out; uint8_t *mask_out; int8_t *boards_out; uint8_t *hands_out; int32_t *meta_out;
+  const int8_t *boards0; const uint8_t *hands0; const uint8_t *sides0; const int32_t *mc0; /* optional start positions */
   int next_env;
   long total;
   pthread_mutex_t mu;
@@ -535,13 +536,21 @@ static void *sp_worker(void *arg) {
     pthread_mutex_unlock(&j->mu);
     if (e >= j->n_envs) break;
     orc_reset(g, j->max_moves);
+    if (j->boards0)
+      orc_load(g, j->boards0 + (size_t)e * NSQ, j->hands0 + (size_t)e * 14, j->sides0[e], j->mc0[e], j->max_moves, 0);
     for (int t = 0; t < j->T; t++) {
       int n = gen_legal(g, 0, tmp);
       memset(mask, 0, NACT);
       for (int i = 0; i < n; i++) mask[tmp[i]] = 1;
       qsort(tmp, n, sizeof(uint16_t), cmp_u16);
       uint32_t r = orc_rand32(j->seed, (uint64_t)(j->env0 + e), (uint64_t)(j->step0 + t));
-      int a = tmp[((uint64_t)r * (uint64_t)n) >> 32];
+      int a = n ? tmp[((uint64_t)r * (uint64_t)n) >> 32] : -1;
+      if (n == 0) { /* loaded position without a legal move: the caller filters these out */
+        size_t ix0 = (size_t)t * j->n_envs + e;
+        if (j->actions) j->actions[ix0] = -1;
+        if (j->legal_counts) j->legal_counts[ix0] = 0;
+        continue;
+      }
       float o4[4];
       orc_make_move(g, a, o4);
       orc_observation(g, obs);
@@ -573,9 +582,11 @@ static void *sp_worker(void *arg) {
 long orc_selfplay(int n_envs, int env0, int T, int step0, int max_moves, uint64_t seed, int32_t *actions,
                   float *rewards, uint8_t *dones, uint8_t *reasons, int32_t *legal_counts,
                   float *obs_out, uint8_t *mask_out, int8_t *boards_out, uint8_t *hands_out,
-                  int32_t *meta_out, int n_threads) {
+                  int32_t *meta_out, int n_threads, const int8_t *boards0, const uint8_t *hands0,
+                  const uint8_t *sides0, const int32_t *mc0) {
   sp_job j = {n_envs, env0, T, step0, max_moves, seed, actions, rewards, dones, reasons, legal_counts,
-              obs_out, mask_out, boards_out, hands_out, meta_out, 0, 0, PTHREAD_MUTEX_INITIALIZER};
+              obs_out, mask_out, boards_out, hands_out, meta_out, boards0, hands0, sides0, mc0,
+              0, 0, PTHREAD_MUTEX_INITIALIZER};
   if (n_threads < 1) n_threads = 1;
   if (n_threads > 256) n_threads = 256;
   pthread_t th[256];

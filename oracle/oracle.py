@@ -62,7 +62,7 @@ def lib() -> C.CDLL:
         L.orc_rand32.restype = C.c_uint32
         L.orc_pick_action.argtypes = [vp, u64, u64, u64]
         L.orc_pick_action.restype = i32
-        L.orc_selfplay.argtypes = [i32, i32, i32, i32, i32, u64] + [vp] * 10 + [i32]
+        L.orc_selfplay.argtypes = [i32, i32, i32, i32, i32, u64] + [vp] * 10 + [i32] + [vp] * 4
         L.orc_selfplay.restype = C.c_long
         L.orc_batch_new.argtypes = [i32, i32]
         L.orc_batch_new.restype = vp
@@ -196,8 +196,9 @@ def rand32(seed: int, env: int, step: int) -> int:
 
 
 def selfplay(n_envs: int, T: int, *, env0: int = 0, step0: int = 0, max_moves: int = 500, seed: int = 1234,
-             threads: int = 1, want_traces: bool = True, want_final: bool = True):
-    """Random-legal self-play with auto-reset (CPU mirror of BASELINE config 2)."""
+             threads: int = 1, want_traces: bool = True, want_final: bool = True, start=None):
+    """Random-legal self-play with auto-reset (CPU mirror of BASELINE config 2).  ``start`` = optional
+    (boards [n,81] int8, hands [n,14] uint8, sides [n] uint8, move_counts [n] int32) initial positions."""
     L = lib()
     out = {}
     if want_traces:
@@ -215,7 +216,10 @@ def selfplay(n_envs: int, T: int, *, env0: int = 0, step0: int = 0, max_moves: i
     g = out.get
     total = L.orc_selfplay(n_envs, env0, T, step0, max_moves, seed, _p(g("actions")), _p(g("rewards")),
                            _p(g("dones")), _p(g("reasons")), _p(g("legal_counts")), _p(g("obs")),
-                           _p(g("mask")), _p(g("boards")), _p(g("hands")), _p(g("meta")), threads)
+                           _p(g("mask")), _p(g("boards")), _p(g("hands")), _p(g("meta")), threads,
+                           *([None] * 4 if start is None else [
+                               _p(np.ascontiguousarray(start[0], np.int8)), _p(np.ascontiguousarray(start[1], np.uint8)),
+                               _p(np.ascontiguousarray(start[2], np.uint8)), _p(np.ascontiguousarray(start[3], np.int32))]))
     out["total_steps"] = int(total)
     return out
 

@@ -67,6 +67,123 @@ __device__ __forceinline__ BB slide_ray(const Tables& T, int sq, int d, BB occ) 
   return ray;
 }
 
+// Squares next to the king of `me` (on K) that an enemy piece attacks, computed on occupancy `occk`
+// (the caller removes the king itself so that sliders x-ray through its square).  64 (neighbour, direction)
+// ray probes in two warp rounds + 16 knight probes.
+__device__ __noinline__ BB king_danger(const uint32_t tab, const int K, const int me, const BB occk) {
+  const int lane = threadIdx.x & 31;
+  const WarpScratch& ws = s_ws[threadIdx.x >> 5];
+  const Tables T{};
+  const int fwd = me == 0 ? -1 : 1;
+  const BB kingsteps = ld_step(T, CLS_KING, K);
+  uint32_t attacked8 = 0;
+#pragma unroll
+  for (int round = 0; round < 2; round++) {
+    const int item = lane + 32 * round;
+    const int n = item >> 3, d = item & 7, od = (d + 4) & 7;
+    const int Tq = K + dir_delta(n);
+    const bool valid = Tq >= 0 && Tq < 81 && bb_test(kingsteps, Tq);
+    int code = 0, b = -1;
+    if (valid) {
+      BB bl = ld_ray(T, Tq, d) & occk;
+      if (bb_any(bl)) {
+        b = dir_positive(d) ? bb_lsb(bl) : bb_msb(bl);
+        code = ws.board[b];
+      }
+    }
+    const uint32_t inf = __shfl_sync(FULL, tab, code);
+    const bool att = code && code_color(code) != me &&
+                     (((inf >> (8 + od)) & 1) || (b == Tq + dir_delta(d) && ((inf >> od) & 1)));
+    const uint32_t bal = __ballot_sync(FULL, att);
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      if ((bal >> (8 * q)) & 0xFF) attacked8 |= 1u << (round * 4 + q);
+  }
+  {
+    const int n = (lane >> 1) & 7;
+    const int Tq = K + dir_delta(n);
+    bool att = false;
+    if (lane < 16 && Tq >= 0 && Tq < 81 && bb_test(kingsteps, Tq)) {
+      const int tr = sq_row(Tq), tc = Tq - 9 * tr;
+      const int r = tr + 2 * fwd, cc = tc + ((lane & 1) ? 1 : -1);
+      if (r >= 0 && r < 9 && cc >= 0 && cc < 9) att = ws.board[r * 9 + cc] == 3 + 14 * (1 - me);
+    }
+    const uint32_t bal = __ballot_sync(FULL, att);
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      if ((bal >> (2 * q)) & 3) attacked8 |= 1u << q;
+  }
+  BB dg = BB{0, 0, 0};
+  if (lane < 8 && ((attacked8 >> lane) & 1)) dg = bb_bit(K + dir_delta(lane));
+  return BB{__reduce_or_sync(FULL, dg.w0), __reduce_or_sync(FULL, dg.w1), __reduce_or_sync(FULL, dg.w2)};
+}
+
+// Uchifuzume test for the one square a dropped pawn can give check from (D, directly in front of the enemy
+// king on KE), valid when that king is not attacked before the drop (always true after a legal move).  The
+// caller has already placed the pawn on ws.board[D].  With a single adjacent, non-sliding checker the enemy's
+// only replies are (a) a king move to a square the dropper does not attack -- taking the pawn included -- and
+// (b) taking the pawn with a piece that is not pinned; blocks and drops cannot answer an adjacent check, and a
+// pinned piece can never reach D because D lies on a king ray whose first piece is the pawn itself.
+// Equivalent to "generate_all_legal_moves(enemy) is empty" (shogi_rules_logic.py:343-357).
+__device__ __noinline__ bool ufz_fast(const uint32_t tab, const int me, const int KE, const int D, const BB occ,
+                                      const BB own) {
+  const int lane = threadIdx.x & 31;
+  const WarpScratch& ws = s_ws[threadIdx.x >> 5];
+  const Tables T{};
+  const int en = 1 - me;
+  const BB occp = occ | bb_bit(D);
+  // (a) king moves
+  const BB danger = king_danger(tab, KE, en, bb_andn(occp, bb_bit(KE)));
+  const BB enemy_pieces = bb_andn(occ, own);
+  const BB kmoves = bb_andn(bb_andn(ld_step(T, CLS_KING, KE), enemy_pieces), danger);
+  if (bb_any(kmoves)) return false;
+  // (b) captures of the pawn by a non-king enemy piece
+  const int kr = sq_row(KE), kc = KE - 9 * kr;
+  int b = -1;
+  {
+    const int d = lane & 7, od = (d + 4) & 7;
+    int code = 0, bb = -1;
+    if (lane < 8) {
+      BB bl = ld_ray(T, D, d) & occp;
+      if (bb_any(bl)) {
+        bb = dir_positive(d) ? bb_lsb(bl) : bb_msb(bl);
+        code = ws.board[bb];
+      }
+    } else if (lane < 10) {  // enemy knights jumping onto D
+      const int dr = sq_row(D), dc = D - 9 * dr;
+      const int r = dr - 2 * (en == 0 ? -1 : 1), cc = dc + (lane == 8 ? -1 : 1);
+      if (r >= 0 && r < 9 && cc >= 0 && cc < 9 && ws.board[r * 9 + cc] == 3 + 14 * en) { bb = r * 9 + cc; code = 3 + 14 * en; }
+    }
+    const uint32_t inf = __shfl_sync(FULL, tab, code);
+    if (code && code_color(code) == en && !((inf >> 23) & 1)) {
+      if (lane >= 8) b = bb;
+      else if (((inf >> (8 + od)) & 1) || (bb == D + dir_delta(d) && ((inf >> od) & 1))) b = bb;
+    }
+  }
+  // pinned?  b must be the first piece on a king ray with a dropper's slider right behind it
+  bool pinned = false;
+  int code3 = 0, d2 = -1;
+  if (b >= 0) {
+    const int br = sq_row(b), bc = b - 9 * br;
+    const int dr = br - kr, dc = bc - kc;
+    if (dr == 0) d2 = dc > 0 ? 2 : 6;
+    else if (dc == 0) d2 = dr > 0 ? 4 : 0;
+    else if (dr == dc) d2 = dr > 0 ? 3 : 7;
+    else if (dr == -dc) d2 = dr > 0 ? 5 : 1;
+    if (d2 >= 0) {
+      const BB ray = ld_ray(T, KE, d2);
+      const BB between = dir_positive(d2) ? (ray & bb_below(b)) : bb_andn(ray, bb_upto(b));
+      if (!bb_any(between & occp)) {
+        const BB beyond = ld_ray(T, b, d2) & occp;
+        if (bb_any(beyond)) code3 = ws.board[dir_positive(d2) ? bb_lsb(beyond) : bb_msb(beyond)];
+      }
+    }
+  }
+  const uint32_t inf3 = __shfl_sync(FULL, tab, code3);
+  if (code3 && code_color(code3) == me && ((inf3 >> (8 + ((d2 + 4) & 7))) & 1)) pinned = true;
+  return !__any_sync(FULL, b >= 0 && !pinned);
+}
+
 struct GenResult {
   int count;
   bool in_check;
@@ -78,12 +195,15 @@ struct GenResult {
 // of can_drop_specific_piece (shogi_rules_logic.py:461-467).  ufz_all: test every pawn-drop square
 // for uchifuzume instead of only the square in front of the enemy king (needed only for loaded
 // positions in which the side NOT to move is already in check).
+#define UFZ_SKIP 0     // is_escape_check mode
+#define UFZ_FAST 1     // specialised evasion test on the square in front of the enemy king (step mode)
+#define UFZ_GENERIC 2  // nested move generation on that square (loaded positions)
+#define UFZ_ALL 3      // nested move generation on every pawn-drop square (enemy king already attacked)
 template <bool EMIT>
-__device__ __noinline__ GenResult gen_moves(const uint32_t tab, const int me, const bool skip_ufz, const bool ufz_all);
+__device__ __noinline__ GenResult gen_moves(const uint32_t tab, const int me, const int ufz_mode);
 
 template <bool EMIT>
-__device__ __forceinline__ GenResult gen_moves_impl(const uint32_t tab, const int me, const bool skip_ufz,
-                                                    const bool ufz_all) {
+__device__ __forceinline__ GenResult gen_moves_impl(const uint32_t tab, const int me, const int ufz_mode) {
   constexpr int SCR = EMIT ? 0 : 1;  // scratch set: the count-only instance runs inside the emitting one
   const int lane = threadIdx.x & 31;
   WarpScratch& ws = s_ws[threadIdx.x >> 5];
@@ -188,73 +308,38 @@ __device__ __forceinline__ GenResult gen_moves_impl(const uint32_t tab, const in
   }
   res.in_check = nchk > 0;
 
-  BB DANGER;  // king targets attacked by the enemy once the king has left its square
-  const BB kingsteps = ld_step(T, CLS_KING, K);
-  {
-    const BB occk = bb_andn(occ, bb_bit(K));
-    uint32_t attacked8 = 0;
-#pragma unroll
-    for (int round = 0; round < 2; round++) {
-      const int item = lane + 32 * round;
-      const int n = item >> 3, d = item & 7, od = (d + 4) & 7;
-      const int Tq = K + dir_delta(n);
-      const bool valid = Tq >= 0 && Tq < 81 && bb_test(kingsteps, Tq);
-      int code = 0, b = -1;
-      if (valid) {
-        BB bl = ld_ray(T, Tq, d) & occk;
-        if (bb_any(bl)) {
-          b = dir_positive(d) ? bb_lsb(bl) : bb_msb(bl);
-          code = ws.board[b];
-        }
-      }
-      const uint32_t inf = __shfl_sync(FULL, tab, code);
-      const bool att = code && code_color(code) != me &&
-                       (((inf >> (8 + od)) & 1) || (b == Tq + dir_delta(d) && ((inf >> od) & 1)));
-      const uint32_t bal = __ballot_sync(FULL, att);
-#pragma unroll
-      for (int q = 0; q < 4; q++)
-        if ((bal >> (8 * q)) & 0xFF) attacked8 |= 1u << (round * 4 + q);
-    }
-    {
-      const int n = (lane >> 1) & 7;
-      const int Tq = K + dir_delta(n);
-      bool att = false;
-      if (lane < 16 && Tq >= 0 && Tq < 81 && bb_test(kingsteps, Tq)) {
-        const int tr = sq_row(Tq), tc = Tq - 9 * tr;
-        const int r = tr + 2 * fwd, cc = tc + ((lane & 1) ? 1 : -1);
-        if (r >= 0 && r < 9 && cc >= 0 && cc < 9) att = ws.board[r * 9 + cc] == 3 + 14 * (1 - me);
-      }
-      const uint32_t bal = __ballot_sync(FULL, att);
-#pragma unroll
-      for (int q = 0; q < 8; q++)
-        if ((bal >> (2 * q)) & 3) attacked8 |= 1u << q;
-    }
-    BB dg = BB{0, 0, 0};
-    if (lane < 8 && ((attacked8 >> lane) & 1)) dg = bb_bit(K + dir_delta(lane));
-    DANGER = BB{__reduce_or_sync(FULL, dg.w0), __reduce_or_sync(FULL, dg.w1), __reduce_or_sync(FULL, dg.w2)};
-  }
+  // king targets attacked by the enemy once the king has left its square
+  const BB DANGER = king_danger(tab, K, me, bb_andn(occ, bb_bit(K)));
   __syncwarp();
 
   // ---- uchifuzume squares (shogi_rules_logic.py:275-359).  A dropped pawn gives check only from the
   // square in front of the enemy king, unless that king is already attacked (loaded positions only).
   BB UFZ = BB{0, 0, 0};
   if constexpr (EMIT) {
-  if (!skip_ufz && hands[me * 7 + 0] > 0 && KE >= 0) {
+  if (ufz_mode != UFZ_SKIP && hands[me * 7 + 0] > 0 && KE >= 0 && nchk < 2) {
     const int last = me == 0 ? 0 : 8;
-    const int lo = ufz_all ? 0 : KE - 9 * fwd;
-    const int hi = ufz_all ? 80 : KE - 9 * fwd;
+    const bool all = ufz_mode == UFZ_ALL;
+    const int lo = all ? 0 : KE - 9 * fwd;
+    const int hi = all ? 80 : KE - 9 * fwd;
     for (int D = lo; D <= hi; D++) {  // warp-uniform loop
       if (D < 0 || D > 80) continue;
       const int dr = sq_row(D), dc = D - 9 * dr;
       if (ws.board[D] != 0 || dr == last || ((pawn_cols >> dc) & 1)) continue;
+      if (nchk == 1 && !bb_test(CM, D)) continue;  // the drop is illegal anyway: it does not answer the check
       __syncwarp();
       if (lane == 0) ws.board[D] = (uint8_t)pcode;
       __syncwarp();
-      GenResult sub = gen_moves<false>(tab, 1 - me, true, false);
+      bool mate;
+      if (ufz_mode == UFZ_FAST) {
+        mate = ufz_fast(tab, me, KE, D, occ, own);
+      } else {
+        GenResult sub = gen_moves<false>(tab, 1 - me, UFZ_SKIP);
+        mate = sub.in_check && sub.count == 0;
+      }
       __syncwarp();
       if (lane == 0) ws.board[D] = 0;
       __syncwarp();
-      if (sub.in_check && sub.count == 0) UFZ = UFZ | bb_bit(D);
+      if (mate) UFZ = UFZ | bb_bit(D);
     }
   }
   }
@@ -375,8 +460,8 @@ __device__ __forceinline__ GenResult gen_moves_impl(const uint32_t tab, const in
 }
 
 template <bool EMIT>
-__device__ __noinline__ GenResult gen_moves(const uint32_t tab, const int me, const bool skip_ufz, const bool ufz_all) {
-  return gen_moves_impl<EMIT>(tab, me, skip_ufz, ufz_all);
+__device__ __noinline__ GenResult gen_moves(const uint32_t tab, const int me, const int ufz_mode) {
+  return gen_moves_impl<EMIT>(tab, me, ufz_mode);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -598,12 +683,20 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
     }
 
     // ---- legal moves of the position now on the board
-    const bool ufz_all = (P.mode == 0);  // loaded positions may have the side not to move in check
-    GenResult gr = gen_moves<true>(tab, side, false, false);
-    if (ufz_all) {
-      // anomaly test: only when the opponent's king is attacked can a pawn drop elsewhere "give check"
-      GenResult opp = gen_moves<false>(tab, 1 - side, true, false);
-      if (opp.in_check && ws.meta[side * 7] > 0) gr = gen_moves<true>(tab, side, false, true);
+    // After a legal move the side that just moved is never in check, so a dropped pawn can only give check from
+    // the square in front of the enemy king and the specialised test applies.  Loaded positions (refresh mode)
+    // may have the side NOT to move in check: they take the nested-generation path, on every pawn-drop square
+    // when that king is attacked.
+    GenResult gr;
+    if (P.mode == 1) {
+      gr = gen_moves<true>(tab, side, UFZ_FAST);
+    } else {
+      int mode = UFZ_GENERIC;
+      if (ws.meta[side * 7] > 0) {
+        GenResult opp = gen_moves<false>(tab, 1 - side, UFZ_SKIP);
+        if (opp.in_check) mode = UFZ_ALL;
+      }
+      gr = gen_moves<true>(tab, side, mode);
     }
 
     if ((moved || (P.mode == 0 && P.eval_term)) && status == 0) {
@@ -753,31 +846,27 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
       else if (lane == 15) pv = max_moves > 0 ? (float)((double)move_count / (double)max_moves) : 0.f;
       const int mis = ((uintptr_t)orow & 15) ? 2 : 0;  // rows are 8-byte aligned; odd rows start 8 past a 16-byte line
       float4* o4 = reinterpret_cast<float4*>(orow + mis);
-      // float4 chunk q covers floats [mis + 4q, mis + 4q + 4).  Chunks 0..565 lie inside the 28 board planes
-      // (floats < 2268): zero fill, the pieces are scattered afterwards.  Chunks 566..930 carry the constant planes.
+      // Zero-fill the whole row with 128-bit stores (float4 chunk q covers floats [mis + 4q, mis + 4q + 4)), then
+      // overwrite what is not zero: the constant planes with a non-zero value (a few of the 18) and one float
+      // per piece.  Both overwrites follow the zero fill in program order behind a __syncwarp().
       const float4 zf = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 2
-      for (int q = lane; q < 566; q += 32) o4[q] = zf;
-#pragma unroll 1
-      for (int it = 0; it < 12; it++) {  // 12 x 32 >= 365 chunks; uniform trip count keeps the shuffles convergent
-        const int q = 566 + it * 32 + lane;
-        const int x0 = mis + 4 * q - 2268;               // >= -4: index into the constant planes
-        const int xa = x0 < 0 ? 0 : x0, xb = x0 + 3;
-        const int pa = (xa * 1619) >> 17, pb = (xb * 1619) >> 17;   // floor(x / 81) for x < 1600
-        const float va = __shfl_sync(FULL, pv, pa & 31), vb = __shfl_sync(FULL, pv, pb & 31);
-        const int edge = pb * 81 - x0;                    // first float of the chunk that lies in plane pb
-        float4 v;  // floats with a negative index still belong to board plane 27 (zero here)
-        v.x = x0 < 0 ? 0.f : (0 >= edge ? vb : va);
-        v.y = x0 + 1 < 0 ? 0.f : (1 >= edge ? vb : va);
-        v.z = x0 + 2 < 0 ? 0.f : (2 >= edge ? vb : va);
-        v.w = x0 + 3 < 0 ? 0.f : vb;
-        if (q < 931) o4[q] = v;
-      }
+      for (int q = lane; q < 931; q += 32) o4[q] = zf;
       if (lane == 0) {  // the 2 floats the float4 grid does not cover: plane 0 head or plane 45 tail, both 0 here
         float2* o2 = reinterpret_cast<float2*>(orow + (mis ? 0 : 3724));
         *o2 = make_float2(0.f, 0.f);
       }
       __syncwarp();
+      uint32_t nzp = __ballot_sync(FULL, pv != 0.f);  // constant planes 28 + i with a non-zero value
+      while (nzp) {
+        const int i = __ffs(nzp) - 1;
+        nzp &= nzp - 1;
+        const float v = __shfl_sync(FULL, pv, i);
+        float* pl = orow + (28 + i) * 81;
+        pl[lane] = v;
+        pl[lane + 32] = v;
+        if (lane < 17) pl[lane + 64] = v;
+      }
 #pragma unroll
       for (int j = 0; j < 3; j++) {
         const int sq = lane + 32 * j;

@@ -234,3 +234,116 @@ def test_illegal_actions_set_error_bits():
     b1, h1, m1 = env.export()
     assert torch.equal(b0, b1) and torch.equal(h0, h1) and torch.equal(m0[:, :5], m1[:, :5])
     assert int(out["done"].sum()) == 0 and float(out["reward"].abs().sum()) == 0.0
+
+
+def _random_endgames(n, seed):
+    """Drop-heavy endgame positions: two kings, a few random pieces, pieces in both hands (BASELINE config 5's
+    'drops-heavy endgames').  Filtered with the oracle so that the side not to move is not in check and the
+    side to move has a legal move."""
+    rng = np.random.default_rng(seed)
+    boards, hands, sides = [], [], []
+    types = [0, 0, 0, 1, 2, 3, 4, 4, 5, 6, 8, 9, 10, 11, 12, 13]
+    while len(boards) < n:
+        b = np.zeros(81, np.int8)
+        k0, k1 = rng.choice(81, 2, replace=False)
+        if max(abs(k0 // 9 - k1 // 9), abs(k0 % 9 - k1 % 9)) < 2:
+            continue
+        b[k0], b[k1] = 8, 22
+        for color in (0, 1):
+            for _ in range(int(rng.integers(0, 6))):
+                sq = int(rng.integers(0, 81))
+                t = int(rng.choice(types))
+                r = sq // 9
+                if b[sq] != 0:
+                    continue
+                last, second = (0, 1) if color == 0 else (8, 7)
+                if t in (0, 1) and r == last:
+                    continue
+                if t == 2 and r in (last, second):
+                    continue
+                if t == 0 and any(b[rr * 9 + sq % 9] == 1 + 14 * color for rr in range(9)):
+                    continue
+                b[sq] = 1 + t + 14 * color
+        h = np.zeros(14, np.uint8)
+        for color in (0, 1):
+            h[color * 7 + 0] = rng.integers(0, 5)
+            for t in range(1, 7):
+                h[color * 7 + t] = rng.integers(0, 3) if rng.random() < 0.5 else 0
+        side = int(rng.integers(0, 2))
+        g = orc.OracleGame.from_arrays(b, h, side, 0, 500, evaluate_termination=False)
+        if g.in_check(1 - side) or len(g.legal_indices()) == 0:
+            continue
+        boards.append(b); hands.append(h); sides.append(side)
+    return np.stack(boards), np.stack(hands), np.asarray(sides, np.uint8), np.zeros(n, np.int32)
+
+
+def test_selfplay_from_drop_heavy_endgames():
+    """Step-mode parity from drop-heavy endgames: exercises the specialised uchifuzume test, drops that answer
+    checks, promoted sliders, and auto-reset back to the start position."""
+    from shogidrl_b200 import VecShogiEnv
+
+    dev = torch.device("cuda:0")
+    n, T, max_moves, seed = 2048, 70, 60, 97
+    start = _random_endgames(n, 5)
+    env = VecShogiEnv(n, max_moves_per_game=max_moves, device=dev, seed=seed, auto_reset=True)
+    env.load_positions(*start, eval_termination=False)
+    env.step_index = 0
+    env.refresh(random_actions=True)
+    acts, rews, reasons, counts = [], [], [], []
+    for t in range(T):
+        a = env.next_actions.clone()
+        counts.append(env.legal_count.clone())
+        out = env.step(a, random_actions=True)
+        acts.append(a); rews.append(out["reward"].clone()); reasons.append(out["reason"].clone())
+    torch.cuda.synchronize()
+    assert int(env.errors().abs().sum()) == 0
+    ref = orc.selfplay(n, T, max_moves=max_moves, seed=seed, threads=os.cpu_count() or 1, start=start)
+    got_c = torch.stack(counts).cpu().numpy()
+    bad = np.argwhere(got_c != ref["legal_counts"])
+    assert len(bad) == 0, ("first legal-count mismatch (t, env):", bad[:5])
+    assert np.array_equal(torch.stack(acts).cpu().numpy(), ref["actions"])
+    assert np.array_equal(torch.stack(rews).cpu().numpy(), ref["rewards"])
+    assert np.array_equal(torch.stack(reasons).cpu().numpy(), ref["reasons"])
+    b, h, m = [x.cpu().numpy() for x in env.export()]
+    assert np.array_equal(b, ref["boards"]) and np.array_equal(h, ref["hands"])
+    assert np.array_equal(env.mask.cpu().numpy(), ref["mask"]) and np.array_equal(env.obs.cpu().numpy(), ref["obs"])
+    assert (ref["reasons"] == 1).sum() > 0  # checkmates happened
+
+
+def test_uchifuzume_fast_path_agrees_with_nested_generation():
+    """The same positions through refresh mode (nested generation, UFZ_GENERIC) and, one ply later, through
+    step mode (UFZ_FAST) must give the oracle's legal sets; pawn-drop mates must actually occur in the sample."""
+    from shogidrl_b200 import VecShogiEnv
+
+    dev = torch.device("cuda:0")
+    n = 4096
+    start = _random_endgames(n, 11)
+    env = VecShogiEnv(n, max_moves_per_game=500, device=dev, seed=3, auto_reset=False)
+    env.load_positions(*start, eval_termination=False)
+    env.step_index = 0
+    env.refresh(random_actions=True)
+    for t in range(3):
+        env.step(env.next_actions.clone(), random_actions=True)
+    torch.cuda.synchronize()
+    b, h, m = [x.cpu().numpy() for x in env.export()]
+    mask = env.mask.cpu().numpy()
+    ufz_seen = 0
+    for e in range(n):
+        if m[e, 3] != 0:
+            continue
+        g = orc.OracleGame.from_arrays(b[e], h[e], int(m[e, 0]), int(m[e, 1]), 500, evaluate_termination=False)
+        want = g.legal_indices()
+        got = np.nonzero(mask[e])[0]
+        assert np.array_equal(got, want), (e, _explain(b[e], h[e], m[e, 0], got, want))
+        # count positions where a pawn drop in front of the enemy king is excluded although the square is free
+        side = int(m[e, 0])
+        if h[e][side * 7] > 0:
+            ke = np.nonzero(b[e] == (22 if side == 0 else 8))[0]
+            if len(ke):
+                D = int(ke[0]) + (9 if side == 0 else -9)
+                if 0 <= D < 81 and b[e][D] == 0 and mask[e][12960 + D * 7] == 0:
+                    col = D % 9
+                    nifu = any(b[e][r * 9 + col] == 1 + 14 * side for r in range(9))
+                    if not nifu and D // 9 != (0 if side == 0 else 8) and not g.in_check(side):
+                        ufz_seen += 1
+    assert ufz_seen > 0
