@@ -92,10 +92,13 @@ int kz_export_positions(const void* state, int n, int hist_cap, int8_t* boards, 
  *         order, k = mulhi(rand32(seed, env_offset+env, rng_step), count)); int64 if
  *         actions_i64 else int32; -1 when there is no legal move.
  * eval_termination != 0 applies _check_and_update_termination_status to loaded positions
- * (shogi_game.py:343, 408-450: mover := opponent of the side to move). */
+ * (shogi_game.py:343, 408-450: mover := opponent of the side to move).
+ * in_check (optional, u8 per env): the side to move is in check (is_in_check,
+ * shogi_rules_logic.py:36-67; a missing king counts as in check). */
 int kz_refresh(void* state, int n, int hist_cap, float* obs, int64_t obs_stride, uint8_t* mask,
                int64_t mask_stride, int32_t* legal_count, void* next_actions, int actions_i64,
-               uint64_t seed, uint32_t rng_step, uint32_t env_offset, int eval_termination, void* stream);
+               uint64_t seed, uint32_t rng_step, uint32_t env_offset, int eval_termination,
+               uint8_t* in_check, void* stream);
 
 /* One environment step for n games: ShogiGame.make_move (shogi_game.py:574-660) fused with the
  * legal-move generation, termination test, mask and observation of the successor, plus what
@@ -117,6 +120,11 @@ int kz_step(void* state, int n, int hist_cap, const void* actions, int actions_i
 int kz_legal_mask(void* state, int n, int hist_cap, uint8_t* mask, int64_t mask_stride,
                   int32_t* legal_count, void* stream);
 int kz_observe(void* state, int n, int hist_cap, float* obs, int64_t obs_stride, void* stream);
+
+/* generate_piece_potential_moves (shogi_rules_logic.py:82-208) for the piece on squares[env]:
+ * targets3 [n][3] uint32 = 81-bit set of pseudo-legal target squares (bit = row*9 + col). */
+int kz_piece_targets(const void* state, int n, int hist_cap, const int32_t* squares, uint32_t* targets3,
+                     void* stream);
 
 /* Per-env error bits (KZ_ERR_*) -> out[n] int32; clear != 0 resets them. */
 int kz_errors(void* state, int n, int hist_cap, int32_t* out, int clear, void* stream);

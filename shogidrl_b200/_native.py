@@ -20,7 +20,7 @@ REASONS = {0: None, 1: "Tsumi", 2: "stalemate", 3: "Max moves reached", 4: "Senn
 
 EXPORTS = [
     "kz_abi_version", "kz_last_cuda_error", "kz_init_tables", "kz_state_layout", "kz_reset", "kz_load_positions",
-    "kz_export_positions", "kz_refresh", "kz_step", "kz_legal_mask", "kz_observe", "kz_errors", "kz_sample_masked",
+    "kz_export_positions", "kz_piece_targets", "kz_refresh", "kz_step", "kz_legal_mask", "kz_observe", "kz_errors", "kz_sample_masked",
     "kz_gae", "kz_gae_exact",
 ]
 
@@ -51,11 +51,12 @@ def lib() -> C.CDLL:
     L.kz_reset.argtypes = [vp, i32, i32, vp, i32, vp]
     L.kz_load_positions.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp]
     L.kz_export_positions.argtypes = [vp, i32, i32, vp, vp, vp, vp]
-    L.kz_refresh.argtypes = [vp, i32, i32, vp, i64, vp, i64, vp, vp, i32, u64, u32, u32, i32, vp]
+    L.kz_refresh.argtypes = [vp, i32, i32, vp, i64, vp, i64, vp, vp, i32, u64, u32, u32, i32, vp, vp]
     L.kz_step.argtypes = [vp, i32, i32, vp, i32, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, vp]
     L.kz_legal_mask.argtypes = [vp, i32, i32, vp, i64, vp, vp]
     L.kz_observe.argtypes = [vp, i32, i32, vp, i64, vp]
     L.kz_errors.argtypes = [vp, i32, i32, vp, i32, vp]
+    L.kz_piece_targets.argtypes = [vp, i32, i32, vp, vp, vp]
     L.kz_sample_masked.argtypes = [vp, i32, i64, vp, i64, i32, u64, u64, vp, i32, vp, vp, i32, vp]
     L.kz_gae.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp, vp]
     L.kz_gae_exact.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp, vp]

@@ -1,0 +1,141 @@
+"""Actor-critic base class and the two reference model families.
+
+``get_action_and_value`` keeps the signature of keisei/core/base_actor_critic.py:43-116 but, after the PyTorch
+forward pass (the only dense contraction on the path), the masked softmax / Categorical sample / log-prob run in
+one hand-written kernel (kz_sample_masked).  ``evaluate_actions`` (:118-184) needs gradients and stays in PyTorch
+with the same formulas (Categorical(probs) clamps probabilities to [eps, 1 - eps] before the log).
+
+Models: ``ActorCritic`` (keisei/core/neural_network.py:10-29) and ``ActorCriticResTower`` with optional
+squeeze-excitation (keisei/training/models/resnet_tower.py:15-84).  Parameter names match the reference so that
+its checkpoints load."""
+from __future__ import annotations
+
+import itertools
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import rl
+
+_EPS = torch.finfo(torch.float32).eps
+_sample_counter = itertools.count()
+
+
+class BaseActorCriticModel(nn.Module):
+    sample_seed: int = 0x5EED
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:  # pragma: no cover - abstract
+        raise NotImplementedError("Subclasses must implement forward method")
+
+    def get_action_and_value(self, obs: torch.Tensor, legal_mask: Optional[torch.Tensor] = None,
+                             deterministic: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        logits, value = self.forward(obs)
+        if legal_mask is None:
+            legal_mask = torch.ones_like(logits, dtype=torch.bool)
+        elif legal_mask.dim() == 1:
+            legal_mask = legal_mask.unsqueeze(0)
+        if legal_mask.shape[0] != logits.shape[0]:
+            legal_mask = legal_mask.expand(logits.shape[0], -1)
+        if logits.dtype not in (torch.float32, torch.bfloat16):
+            logits = logits.float()
+        n = logits.shape[0]
+        offset = next(_sample_counter) * (1 << 20)
+        action, log_prob, _ = rl.sample_masked(logits.contiguous(), legal_mask, seed=self.sample_seed, offset=offset,
+                                               deterministic=deterministic)
+        if value.dim() > 1 and value.shape[-1] == 1:
+            value = value.squeeze(-1)
+        return action, log_prob, value
+
+    def evaluate_actions(self, obs: torch.Tensor, actions: torch.Tensor, legal_mask: Optional[torch.Tensor] = None
+                         ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        logits, value = self.forward(obs)
+        return self.evaluate_from_logits(logits, value, actions, legal_mask)
+
+    @staticmethod
+    def evaluate_from_logits(logits: torch.Tensor, value: torch.Tensor, actions: torch.Tensor,
+                             legal_mask: Optional[torch.Tensor] = None):
+        """log-prob / entropy / value from a forward pass that may have gone through a DDP wrapper."""
+        logits = logits.float()
+        if legal_mask is not None:
+            logits = torch.where(legal_mask.bool(), logits, torch.full((), float("-inf"), device=logits.device))
+        probs = F.softmax(logits, dim=-1)
+        nan_rows = torch.isnan(probs).any(dim=1, keepdim=True)
+        probs = torch.where(nan_rows, torch.full_like(probs, 1.0 / probs.shape[-1]), probs)
+        log_p = torch.log(probs.clamp(min=_EPS, max=1.0 - _EPS))  # Categorical(probs=...).logits
+        log_probs = log_p.gather(1, actions.long().unsqueeze(1)).squeeze(1)
+        entropy = -(probs * log_p).sum(dim=-1)
+        if value.dim() > 1 and value.shape[-1] == 1:
+            value = value.squeeze(-1)
+        return log_probs, entropy, value
+
+
+class ActorCritic(BaseActorCriticModel):
+    """Conv(46->16, 3x3) + ReLU + Flatten + Linear heads (BASELINE config 3's "default CNN")."""
+
+    def __init__(self, input_channels: int, num_actions_total: int):
+        super().__init__()
+        self.conv = nn.Conv2d(input_channels, 16, kernel_size=3, padding=1)
+        self.relu = nn.ReLU()
+        self.flatten = nn.Flatten()
+        self.policy_head = nn.Linear(16 * 81, num_actions_total)
+        self.value_head = nn.Linear(16 * 81, 1)
+
+    def forward(self, x):
+        x = self.flatten(self.relu(self.conv(x)))
+        return self.policy_head(x), self.value_head(x)
+
+
+class SqueezeExcitation(nn.Module):
+    def __init__(self, channels: int, se_ratio: float = 0.25):
+        super().__init__()
+        hidden = max(1, int(channels * se_ratio))
+        self.fc1 = nn.Conv2d(channels, hidden, 1)
+        self.fc2 = nn.Conv2d(hidden, channels, 1)
+
+    def forward(self, x):
+        s = torch.sigmoid(self.fc2(F.relu(self.fc1(F.adaptive_avg_pool2d(x, 1)))))
+        return x * s
+
+
+class ResidualBlock(nn.Module):
+    def __init__(self, channels: int, se_ratio: Optional[float] = None):
+        super().__init__()
+        self.conv1 = nn.Conv2d(channels, channels, 3, padding=1)
+        self.bn1 = nn.BatchNorm2d(channels)
+        self.conv2 = nn.Conv2d(channels, channels, 3, padding=1)
+        self.bn2 = nn.BatchNorm2d(channels)
+        self.se = SqueezeExcitation(channels, se_ratio) if se_ratio else None
+
+    def forward(self, x):
+        out = self.bn2(self.conv2(F.relu(self.bn1(self.conv1(x)))))
+        if self.se is not None:
+            out = self.se(out)
+        return F.relu(out + x)
+
+
+class ActorCriticResTower(BaseActorCriticModel):
+    def __init__(self, input_channels: int, num_actions_total: int, tower_depth: int = 9, tower_width: int = 256,
+                 se_ratio: Optional[float] = None):
+        super().__init__()
+        self.stem = nn.Conv2d(input_channels, tower_width, 3, padding=1)
+        self.bn_stem = nn.BatchNorm2d(tower_width)
+        self.res_blocks = nn.Sequential(*[ResidualBlock(tower_width, se_ratio) for _ in range(tower_depth)])
+        self.policy_head = nn.Sequential(nn.Conv2d(tower_width, 2, 1), nn.BatchNorm2d(2), nn.ReLU(), nn.Flatten(),
+                                         nn.Linear(2 * 81, num_actions_total))
+        self.value_head = nn.Sequential(nn.Conv2d(tower_width, 2, 1), nn.BatchNorm2d(2), nn.ReLU(), nn.Flatten(),
+                                        nn.Linear(2 * 81, 1))
+
+    def forward(self, x):
+        x = self.res_blocks(F.relu(self.bn_stem(self.stem(x))))
+        return self.policy_head(x), self.value_head(x).squeeze(-1)
+
+
+def model_factory(model_type, obs_shape, num_actions, tower_depth, tower_width, se_ratio, **kwargs):
+    """keisei/training/models/__init__.py:6-31."""
+    if model_type == "resnet":
+        return ActorCriticResTower(obs_shape[0], num_actions, tower_depth, tower_width, se_ratio, **kwargs)
+    if model_type in ("dummy", "testmodel", "resumemodel"):
+        return ActorCriticResTower(obs_shape[0], num_actions, 1, 16, None, **kwargs)
+    raise ValueError(f"Unknown model_type: {model_type}")

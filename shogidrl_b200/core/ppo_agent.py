@@ -1,0 +1,244 @@
+"""PPOAgent -- API of keisei/core/ppo_agent.py (select_action :134-223, get_value :225-241, learn :243-460,
+save/load :462-534) on top of the device kernels.
+
+* ``select_action`` / ``select_actions``: PyTorch forward (bf16 autocast optional) + kz_sample_masked.
+* ``learn``: PPO-clip in PyTorch (the dense path stays PyTorch by design), whole-buffer advantage normalisation,
+  numpy-seeded minibatch shuffling exactly as the reference; under torch.distributed the normalisation statistics
+  are all-reduced so that sharded rollouts normalise like one big buffer."""
+from __future__ import annotations
+
+import copy
+import os
+import sys
+from typing import Any, Dict, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from ..utils.policy_mapper import PolicyOutputMapper
+
+
+def _log(level: str, msg: str) -> None:
+    print(f"[PPOAgent] {level}: {msg}", file=sys.stderr)
+
+
+def _make_scheduler(optimizer, schedule_type, total_steps, kwargs):
+    """Minimal counterpart of keisei/core/scheduler_factory.py:11-110."""
+    if not schedule_type:
+        return None
+    kwargs = dict(kwargs or {})
+    total_steps = max(1, int(total_steps))
+    if schedule_type == "linear":
+        final = kwargs.get("final_lr_fraction", 0.1)
+        return torch.optim.lr_scheduler.LambdaLR(optimizer, lambda s: 1.0 - (1.0 - final) * min(s, total_steps) / total_steps)
+    if schedule_type == "cosine":
+        base = optimizer.param_groups[0]["lr"]
+        return torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, T_max=total_steps,
+                                                          eta_min=base * kwargs.get("eta_min_fraction", 0.0))
+    if schedule_type == "exponential":
+        return torch.optim.lr_scheduler.ExponentialLR(optimizer, gamma=kwargs.get("gamma", 0.995))
+    if schedule_type == "step":
+        return torch.optim.lr_scheduler.StepLR(optimizer, step_size=kwargs.get("step_size", max(1, total_steps // 3)),
+                                               gamma=kwargs.get("gamma", 0.5))
+    raise ValueError(f"Unsupported scheduler type: {schedule_type}")
+
+
+class PPOAgent:
+    def __init__(self, model, config, device: torch.device, name: str = "PPOAgent", scaler=None,
+                 use_mixed_precision: bool = False):
+        self.config = config.model_copy(deep=True) if hasattr(config, "model_copy") else copy.deepcopy(config)
+        self.device = torch.device(device)
+        self.name = name
+        self.scaler = scaler
+        self.use_mixed_precision = use_mixed_precision
+        self.model = model.to(self.device)
+        self.policy_output_mapper = PolicyOutputMapper()
+        self.num_actions_total = self.policy_output_mapper.get_total_actions()
+        tr = config.training
+        weight_decay = getattr(tr, "weight_decay", 0.0)
+        try:
+            self.optimizer = torch.optim.Adam(self.model.parameters(), lr=tr.learning_rate, weight_decay=weight_decay)
+        except Exception as e:  # same fallback as the reference (ppo_agent.py:72-80)
+            _log("ERROR", f"Could not initialize optimizer with lr={tr.learning_rate}, using default lr=1e-3: {e}")
+            self.optimizer = torch.optim.Adam(self.model.parameters(), lr=1e-3, weight_decay=weight_decay)
+        self.gamma = tr.gamma
+        self.clip_epsilon = tr.clip_epsilon
+        self.value_loss_coeff = tr.value_loss_coeff
+        self.entropy_coef = tr.entropy_coef
+        self.ppo_epochs = tr.ppo_epochs
+        self.minibatch_size = tr.minibatch_size
+        self.normalize_advantages = getattr(tr, "normalize_advantages", True)
+        self.enable_value_clipping = getattr(tr, "enable_value_clipping", False)
+        self.gradient_clip_max_norm = tr.gradient_clip_max_norm
+        self.last_kl_div = 0.0
+        self.last_gradient_norm = 0.0
+        self._rng = np.random.default_rng(getattr(config.env, "seed", None))
+        self.lr_schedule_type = getattr(tr, "lr_schedule_type", None)
+        self.lr_schedule_step_on = getattr(tr, "lr_schedule_step_on", "epoch")
+        epochs = max(1, getattr(tr, "total_timesteps", tr.steps_per_epoch) // tr.steps_per_epoch)
+        if self.lr_schedule_step_on == "epoch":
+            total = epochs * tr.ppo_epochs
+        else:
+            total = epochs * (tr.steps_per_epoch // tr.minibatch_size) * tr.ppo_epochs
+        self.scheduler = _make_scheduler(self.optimizer, self.lr_schedule_type, total,
+                                         getattr(tr, "lr_schedule_kwargs", None))
+
+    # ------------------------------------------------------------------ acting
+    def _is_obs_scaler(self) -> bool:
+        return self.scaler is not None and not isinstance(self.scaler, torch.amp.GradScaler)
+
+    def _scale(self, obs: torch.Tensor) -> torch.Tensor:
+        if self._is_obs_scaler():
+            return self.scaler.transform(obs) if hasattr(self.scaler, "transform") else self.scaler(obs)
+        return obs
+
+    def _autocast(self):
+        return torch.autocast("cuda", dtype=torch.bfloat16, enabled=bool(self.use_mixed_precision and self.device.type == "cuda"))
+
+    def select_actions(self, obs: torch.Tensor, legal_mask: torch.Tensor, *, is_training: bool = True
+                       ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Batched select_action: obs [N,46,9,9] and legal_mask [N,13527] stay on the device; returns
+        (actions int64 [N], log_probs fp32 [N], values fp32 [N]) without any host synchronisation."""
+        self.model.train(is_training)
+        with torch.no_grad(), self._autocast():
+            action, log_prob, value = self.model.get_action_and_value(self._scale(obs), legal_mask=legal_mask,
+                                                                      deterministic=not is_training)
+        return action, log_prob, value.float()
+
+    def select_action(self, obs: np.ndarray, legal_mask: torch.Tensor, *, is_training: bool = True):
+        """(MoveTuple, policy index, log_prob, value) for one observation (ppo_agent.py:134-223)."""
+        obs_tensor = torch.as_tensor(obs, dtype=torch.float32, device=self.device).unsqueeze(0)
+        if not bool(legal_mask.any()):
+            _log("ERROR", "select_action called with no legal moves (based on input legal_mask)")
+        action, log_prob, value = self.select_actions(obs_tensor, legal_mask.to(self.device), is_training=is_training)
+        idx, lp, v = int(action.item()), float(log_prob.item()), float(value.item())
+        try:
+            move = self.policy_output_mapper.policy_index_to_shogi_move(idx)
+        except IndexError as e:
+            _log("ERROR", f"Policy index {idx} out of bounds in select_action: {e}")
+            return None, -1, 0.0, v
+        return move, idx, lp, v
+
+    def get_values(self, obs: torch.Tensor) -> torch.Tensor:
+        self.model.eval()
+        with torch.no_grad(), self._autocast():
+            _, value = self.model(self._scale(obs))
+        if value.dim() > 1 and value.shape[-1] == 1:
+            value = value.squeeze(-1)
+        return value.float()
+
+    def get_value(self, obs_np: np.ndarray) -> float:
+        obs = torch.as_tensor(obs_np, dtype=torch.float32, device=self.device).unsqueeze(0)
+        return float(self.get_values(obs).item())
+
+    # ------------------------------------------------------------------ learning
+    def learn(self, experience_buffer) -> Dict[str, float]:
+        self.model.train()
+        batch = experience_buffer.get_batch()
+        lr = self.optimizer.param_groups[0]["lr"]
+        if not batch or batch["obs"].shape[0] == 0:
+            _log("ERROR", "learn called with empty batch_data")
+            return {"ppo/policy_loss": 0.0, "ppo/value_loss": 0.0, "ppo/entropy": 0.0,
+                    "ppo/kl_divergence_approx": self.last_kl_div, "ppo/learning_rate": lr}
+        d = self.device
+        obs_b, act_b = batch["obs"].to(d), batch["actions"].to(d)
+        oldlp_b, oldv_b = batch["log_probs"].to(d), batch["values"].to(d)
+        adv_b, ret_b, mask_b = batch["advantages"].to(d), batch["returns"].to(d), batch["legal_masks"].to(d)
+        if self.normalize_advantages:
+            adv_b = self._normalize(adv_b)
+        n = obs_b.shape[0]
+        indices = np.arange(n)
+        sums = torch.zeros(5, device=d)  # policy, value, entropy-loss, kl, clip fraction
+        updates = 0
+        for _ in range(self.ppo_epochs):
+            self._rng.shuffle(indices)
+            for start in range(0, n, self.minibatch_size):
+                mb = torch.as_tensor(indices[start:start + self.minibatch_size], device=d)
+                with self._autocast():
+                    logits, values = self._train_forward(self._scale(obs_b[mb]))
+                    new_lp, entropy, new_v = type(self.model).evaluate_from_logits(logits, values, act_b[mb], mask_b[mb])
+                new_v = new_v.float()
+                ratio = torch.exp(new_lp - oldlp_b[mb])
+                adv = adv_b[mb]
+                policy_loss = -torch.min(ratio * adv, torch.clamp(ratio, 1 - self.clip_epsilon, 1 + self.clip_epsilon) * adv).mean()
+                if self.enable_value_clipping:
+                    clipped = oldv_b[mb] + torch.clamp(new_v - oldv_b[mb], -self.clip_epsilon, self.clip_epsilon)
+                    value_loss = torch.max(F.mse_loss(new_v.squeeze(), ret_b[mb].squeeze()),
+                                           F.mse_loss(clipped.squeeze(), ret_b[mb].squeeze()))
+                else:
+                    value_loss = F.mse_loss(new_v.squeeze(), ret_b[mb].squeeze())
+                entropy_loss = -entropy.mean()
+                loss = policy_loss + self.value_loss_coeff * value_loss + self.entropy_coef * entropy_loss
+                self.optimizer.zero_grad(set_to_none=True)
+                loss.backward()  # under DistributedDataParallel the gradient all-reduce (NCCL) fires here
+                gn = torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.gradient_clip_max_norm)
+                self.optimizer.step()
+                if self.scheduler is not None and self.lr_schedule_step_on == "update":
+                    self.scheduler.step()
+                with torch.no_grad():
+                    sums += torch.stack([policy_loss, value_loss, entropy_loss, (oldlp_b[mb] - new_lp).mean(),
+                                         ((ratio - 1.0).abs() > self.clip_epsilon).float().mean()]).detach()
+                    self._gn = gn
+                updates += 1
+        if self.scheduler is not None and self.lr_schedule_step_on == "epoch":
+            self.scheduler.step()
+        avg = (sums / max(1, updates)).tolist()  # one host synchronisation per learn() instead of 5 per minibatch
+        self.last_gradient_norm = float(self._gn) if updates else 0.0
+        self.last_kl_div = avg[3]
+        return {"ppo/policy_loss": avg[0], "ppo/value_loss": avg[1], "ppo/entropy": avg[2],
+                "ppo/kl_divergence_approx": avg[3], "ppo/clip_fraction": avg[4],
+                "ppo/learning_rate": self.optimizer.param_groups[0]["lr"]}
+
+    def enable_ddp(self) -> None:
+        """Wrap the model for the update when torch.distributed is initialised (gradient all-reduce over NCCL)."""
+        from ..training import distributed as kd
+        self._ddp = kd.wrap_ddp(self.model, self.device)
+
+    def _train_forward(self, obs: torch.Tensor):
+        ddp = getattr(self, "_ddp", None)
+        return (ddp if ddp is not None else self.model)(obs)
+
+    def _normalize(self, adv: torch.Tensor) -> torch.Tensor:
+        """Whole-buffer normalisation (ppo_agent.py:276-282: unbiased std, skipped for tiny std / single sample).
+        When rollouts are sharded over ranks, (count, sum, sum of squares) are all-reduced first."""
+        from ..training import distributed as kd
+        cnt, s1, s2 = kd.global_moments(adv)
+        if cnt <= 1:
+            return adv
+        mean = s1 / cnt
+        var = max(0.0, (s2 - cnt * mean * mean) / (cnt - 1))
+        std = var ** 0.5
+        return (adv - mean) / std if std > 1e-8 else adv
+
+    # ------------------------------------------------------------------ checkpoints (format kept as is)
+    def save_model(self, file_path: str, global_timestep: int = 0, total_episodes_completed: int = 0,
+                   stats_to_save: Optional[Dict[str, int]] = None) -> None:
+        model = getattr(self.model, "module", self.model)  # unwrap DistributedDataParallel
+        data = {"model_state_dict": model.state_dict(), "optimizer_state_dict": self.optimizer.state_dict(),
+                "global_timestep": global_timestep, "total_episodes_completed": total_episodes_completed}
+        if stats_to_save:
+            data.update(stats_to_save)
+        if self.scheduler is not None:
+            data.update(scheduler_state_dict=self.scheduler.state_dict(), lr_schedule_type=self.lr_schedule_type,
+                        lr_schedule_step_on=self.lr_schedule_step_on)
+        torch.save(data, file_path)
+
+    def load_model(self, file_path: str) -> Dict[str, Any]:
+        empty = {"global_timestep": 0, "total_episodes_completed": 0, "black_wins": 0, "white_wins": 0, "draws": 0}
+        if not os.path.exists(file_path):
+            _log("ERROR", f"Checkpoint file {file_path} not found")
+            return {**empty, "error": "File not found"}
+        try:
+            ck = torch.load(file_path, map_location=self.device, weights_only=False)
+            getattr(self.model, "module", self.model).load_state_dict(ck["model_state_dict"])
+            self.optimizer.load_state_dict(ck["optimizer_state_dict"])
+            if self.scheduler is not None and "scheduler_state_dict" in ck:
+                self.scheduler.load_state_dict(ck["scheduler_state_dict"])
+            return {k: ck.get(k, v) for k, v in {**empty, "lr_schedule_type": None, "lr_schedule_step_on": "epoch"}.items()}
+        except (KeyError, RuntimeError, EOFError) as e:
+            _log("ERROR", f"Error loading checkpoint from {file_path}: {e}")
+            return {**empty, "error": str(e)}
+
+    def get_name(self) -> str:
+        return self.name

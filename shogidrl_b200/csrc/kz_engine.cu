@@ -519,6 +519,7 @@ struct StepParams {
   int8_t* winner;
   int32_t* ep_len;
   int32_t* legal_count;
+  uint8_t* in_check;  // optional: side to move is in check (ShogiGame.is_in_check)
   void* next_actions;
   unsigned long long seed;
   uint32_t rng_step;
@@ -740,6 +741,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
       if (P.winner) P.winner[g] = (int8_t)winner_out;
       if (P.ep_len) P.ep_len[g] = ep_len_out;
       if (P.legal_count) P.legal_count[g] = gr.count;
+      if (P.in_check) P.in_check[g] = (uint8_t)gr.in_check;
     }
 
     if (P.mask) {
@@ -976,6 +978,40 @@ __global__ void kz_errors_kernel(uint8_t* meta, int n, int32_t* out, int clear) 
   if (clear) meta[(size_t)g * 32 + 17] = 0;
 }
 
+// Pseudo-legal targets of the piece standing on squares[g] (generate_piece_potential_moves,
+// shogi_rules_logic.py:82-208): steps + slides up to the first blocker, own-colour squares removed.
+__global__ void kz_targets_kernel(const uint8_t* boards, int n, const int32_t* squares, uint32_t* out) {
+  for (int i = threadIdx.x; i < 81 * 8 * 3; i += blockDim.x) s_ray[i] = g_ray[i];
+  for (int i = threadIdx.x; i < NCLS * 81 * 3; i += blockDim.x) s_step[i] = g_step[i];
+  __syncthreads();
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (g >= n) return;
+  const Tables T{};
+  const uint8_t* b = boards + (size_t)g * 96;
+  const int sq = squares[g];
+  const uint32_t tab = code_info(lane);
+  const int code = (sq >= 0 && sq < 81) ? b[sq] : 0;
+  const uint32_t inf = __shfl_sync(FULL, tab, code);
+  const int me = code_color(code);
+  uint32_t o[3], w[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const int s = lane + 32 * j;
+    const int c = s < 81 ? b[s] : 0;
+    o[j] = __ballot_sync(FULL, c != 0);
+    w[j] = __ballot_sync(FULL, c != 0 && code_color(c) == me);
+  }
+  BB t = BB{0, 0, 0};
+  if (code) {
+    t = ld_step(T, (inf >> 16) & 15, sq);
+    uint32_t sl = (inf >> 8) & 0xFF;
+    while (sl) { const int d = __ffs(sl) - 1; sl &= sl - 1; t = t | slide_ray(T, sq, d, BB{o[0], o[1], o[2]}); }
+    t = bb_andn(t, BB{w[0], w[1], w[2]});
+  }
+  if (lane == 0) { out[(size_t)g * 3] = t.w0; out[(size_t)g * 3 + 1] = t.w1; out[(size_t)g * 3 + 2] = t.w2; }
+}
+
 thread_local char t_cuda_err[256] = "";
 int cuda_fail(cudaError_t e) {
   snprintf(t_cuda_err, sizeof t_cuda_err, "%s", cudaGetErrorString(e));
@@ -1160,6 +1196,16 @@ int kz_export_positions(const void* state, int n, int hist_cap, int8_t* boards, 
   return KZ_OK;
 }
 
+int kz_piece_targets(const void* state, int n, int hist_cap, const int32_t* squares, uint32_t* targets3, void* stream) {
+  if (!state || n <= 0 || !squares || !targets3) return KZ_E_ARG;
+  if (!g_host_ready) return KZ_E_NOT_INIT;
+  const Layout L = layout(n, hist_cap);
+  const uint8_t* base = reinterpret_cast<const uint8_t*>(state);
+  kz_targets_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(base + L.off_boards, n, squares, targets3);
+  CK(cudaGetLastError());
+  return KZ_OK;
+}
+
 int kz_errors(void* state, int n, int hist_cap, int32_t* out, int clear, void* stream) {
   if (!state || n <= 0 || !out) return KZ_E_ARG;
   const Layout L = layout(n, hist_cap);
@@ -1171,8 +1217,9 @@ int kz_errors(void* state, int n, int hist_cap, int32_t* out, int clear, void* s
 
 int kz_refresh(void* state, int n, int hist_cap, float* obs, int64_t obs_stride, uint8_t* mask, int64_t mask_stride,
                int32_t* legal_count, void* next_actions, int actions_i64, uint64_t seed, uint32_t rng_step,
-               uint32_t env_offset, int eval_termination, void* stream) {
+               uint32_t env_offset, int eval_termination, uint8_t* in_check, void* stream) {
   StepParams P{};
+  P.in_check = in_check;
   P.obs = obs; P.obs_stride = obs_stride; P.mask = mask; P.mask_stride = mask_stride;
   P.legal_count = legal_count; P.next_actions = next_actions; P.actions_i64 = actions_i64;
   P.seed = seed; P.rng_step = rng_step; P.env_offset = env_offset;
@@ -1198,12 +1245,12 @@ int kz_step(void* state, int n, int hist_cap, const void* actions, int actions_i
 int kz_legal_mask(void* state, int n, int hist_cap, uint8_t* mask, int64_t mask_stride, int32_t* legal_count,
                   void* stream) {
   if (!mask && !legal_count) return KZ_E_ARG;
-  return kz_refresh(state, n, hist_cap, nullptr, 0, mask, mask_stride, legal_count, nullptr, 0, 0, 0, 0, 0, stream);
+  return kz_refresh(state, n, hist_cap, nullptr, 0, mask, mask_stride, legal_count, nullptr, 0, 0, 0, 0, 0, nullptr, stream);
 }
 
 int kz_observe(void* state, int n, int hist_cap, float* obs, int64_t obs_stride, void* stream) {
   if (!obs) return KZ_E_ARG;
-  return kz_refresh(state, n, hist_cap, obs, obs_stride, nullptr, 0, nullptr, nullptr, 0, 0, 0, 0, 0, stream);
+  return kz_refresh(state, n, hist_cap, obs, obs_stride, nullptr, 0, nullptr, nullptr, 0, 0, 0, 0, 0, nullptr, stream);
 }
 
 }  // extern "C"

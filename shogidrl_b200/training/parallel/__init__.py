@@ -1,0 +1,115 @@
+"""keisei.training.parallel on a B200: the reference spreads self-play over CPU worker processes that pickle
+tensors through mp.Queue and receive gzip-compressed weights (parallel_manager.py:23-345, self_play_worker.py,
+communication.py, model_sync.py).  Here the games live on the device next to the model, so "workers" are rows of
+one VecShogiEnv batch: ``ParallelManager.collect_experiences(buffer)`` keeps its signature and fills the buffer
+from a batched rollout; model synchronisation is a no-op (same process, same weights)."""
+from __future__ import annotations
+
+import gzip
+from typing import Any, Dict, Optional
+
+import numpy as np
+import torch
+
+from ..step_manager import VecStepManager
+from ...core.experience_buffer import RolloutBuffer
+
+
+def compress_array(array: np.ndarray, compression_level: int = 6) -> Dict[str, Any]:
+    """parallel/utils.py:8-37 (kept for callers that still ship weights between hosts)."""
+    raw = np.ascontiguousarray(array).tobytes()
+    comp = gzip.compress(raw, compresslevel=compression_level)
+    return {"data": comp, "shape": array.shape, "dtype": str(array.dtype), "compressed": True,
+            "original_size": len(raw), "compressed_size": len(comp), "compression_ratio": len(raw) / max(1, len(comp))}
+
+
+def decompress_array(data: Dict[str, Any]) -> np.ndarray:
+    raw = gzip.decompress(data["data"]) if data.get("compressed") else data["data"]
+    return np.frombuffer(raw, dtype=np.dtype(data["dtype"])).reshape(data["shape"]).copy()
+
+
+class ModelSynchronizer:
+    """No-op shim: rollout and update share one model object on one device."""
+
+    def __init__(self, sync_interval: int = 100, compression_enabled: bool = True):
+        self.sync_interval, self.compression_enabled = sync_interval, compression_enabled
+        self.last_sync_step, self.sync_count = 0, 0
+
+    def should_sync(self, current_step: int) -> bool:
+        return current_step - self.last_sync_step >= self.sync_interval
+
+    def mark_sync_completed(self, current_step: int) -> None:
+        self.last_sync_step, self.sync_count = current_step, self.sync_count + 1
+
+    def get_sync_stats(self) -> Dict[str, Any]:
+        return {"sync_count": self.sync_count, "last_sync_step": self.last_sync_step,
+                "sync_interval": self.sync_interval}
+
+
+class ParallelManager:
+    """collect_experiences(buffer) fed by ``num_workers`` device-resident games instead of worker processes."""
+
+    def __init__(self, env_config: Dict[str, Any], model_config: Dict[str, Any], parallel_config: Dict[str, Any],
+                 device: str = "cuda"):
+        self.env_config, self.model_config, self.parallel_config = env_config, model_config, parallel_config
+        self.device = torch.device(device)
+        self.num_workers = int(parallel_config.get("num_workers", 4))
+        self.batch_size = int(parallel_config.get("batch_size", 32))
+        self.model_sync = ModelSynchronizer(parallel_config.get("sync_interval", 100),
+                                            parallel_config.get("compression_enabled", True))
+        self.total_steps_collected = 0
+        self.total_batches_received = 0
+        self.is_running = False
+        self._driver: Optional[VecStepManager] = None
+
+    def start_workers(self, agent, gamma: float = 0.99, lambda_gae: float = 0.95) -> bool:
+        from ...vec_env import VecShogiEnv
+        env = VecShogiEnv(self.num_workers, max_moves_per_game=int(self.env_config.get("max_moves_per_game", 500)),
+                          device=self.device, seed=int(self.env_config.get("seed", 0) or 0))
+        buf = RolloutBuffer(self.batch_size, self.num_workers, gamma, lambda_gae, self.device)
+        self._driver = VecStepManager(env, agent, buf)
+        self._driver.start()
+        self.is_running = True
+        return True
+
+    def collect_experiences(self, experience_buffer) -> int:
+        """One batched rollout of ``batch_size`` steps x ``num_workers`` games appended to ``experience_buffer``
+        (an ExperienceBuffer); returns the number of transitions added."""
+        if not self.is_running or self._driver is None:
+            return 0
+        d = self._driver
+        d.collect()
+        b = d.buffer
+        T, N = b.T, b.N
+        before = experience_buffer.size()
+        experience_buffer.add_from_worker_batch({
+            "obs": b.obs[:T].transpose(0, 1).reshape(T * N, 46, 9, 9), "actions": b.actions.t().reshape(-1),
+            "rewards": b.rewards.t().reshape(-1), "log_probs": b.log_probs.t().reshape(-1),
+            "values": b.values.t().reshape(-1), "dones": b.dones.t().reshape(-1).bool(),
+            "legal_masks": b.masks[:T].transpose(0, 1).reshape(T * N, -1).bool()})
+        b.clear()
+        added = experience_buffer.size() - before
+        self.total_steps_collected += added
+        self.total_batches_received += 1
+        return added
+
+    def sync_model_if_needed(self, model, current_step: int) -> bool:
+        if self.model_sync.should_sync(current_step):
+            self.model_sync.mark_sync_completed(current_step)
+            return True
+        return False
+
+    def stop_workers(self) -> None:
+        self.is_running = False
+        self._driver = None
+
+    def is_healthy(self) -> bool:
+        return self.is_running and self._driver is not None
+
+    def get_parallel_stats(self) -> Dict[str, Any]:
+        return {"num_workers": self.num_workers, "total_steps_collected": self.total_steps_collected,
+                "total_batches_received": self.total_batches_received, "is_running": self.is_running,
+                "sync_stats": self.model_sync.get_sync_stats()}
+
+
+__all__ = ["ParallelManager", "ModelSynchronizer", "compress_array", "decompress_array"]

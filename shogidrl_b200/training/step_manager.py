@@ -1,0 +1,257 @@
+"""StepManager -- per-timestep composition of the reference (keisei/training/step_manager.py:98-348 execute_step,
+:350-481 handle_episode_end, :483-534 reset / update) over injected game / agent / mapper / buffer objects, plus
+``VecStepManager``: the same composition for N device-resident games per kernel launch, where observations and
+masks are written by the engine straight into the [T, N] rollout buffer."""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass
+from typing import Any, Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from ..shogi.definitions import Color
+
+_CAPTURE_VALUE = {"PAWN": 1, "LANCE": 3, "KNIGHT": 3, "SILVER": 5, "GOLD": 6, "BISHOP": 8, "ROOK": 10}
+
+
+@dataclass
+class EpisodeState:
+    current_obs: np.ndarray
+    current_obs_tensor: torch.Tensor
+    episode_reward: float
+    episode_length: int
+
+
+@dataclass
+class StepResult:
+    next_obs: np.ndarray
+    next_obs_tensor: torch.Tensor
+    reward: float
+    done: bool
+    info: Dict[str, Any]
+    selected_move: Optional[Tuple]
+    policy_index: int
+    log_prob: float
+    value_pred: float
+    success: bool = True
+    error_message: Optional[str] = None
+
+
+class StepManager:
+    def __init__(self, config, game, agent, policy_mapper, experience_buffer):
+        self.config = config
+        self.game = game
+        self.agent = agent
+        self.policy_mapper = policy_mapper
+        self.experience_buffer = experience_buffer
+        self.device = torch.device(config.env.device)
+        self.move_history: List[Tuple] = []
+        self.move_log: List[str] = []
+        self._reset_counters()
+
+    def _reset_counters(self) -> None:
+        self.sente_best_capture: Optional[str] = None
+        self.sente_best_capture_value = 0
+        self.gote_best_capture: Optional[str] = None
+        self.gote_best_capture_value = 0
+        self.sente_capture_count = self.gote_capture_count = 0
+        self.sente_drop_count = self.gote_drop_count = 0
+        self.sente_promo_count = self.gote_promo_count = 0
+
+    def _obs_tensor(self, obs: np.ndarray) -> torch.Tensor:
+        return torch.tensor(obs, dtype=torch.float32, device=self.device).unsqueeze(0)
+
+    def _failure(self, obs, done: bool, info: Dict[str, Any], message: str) -> StepResult:
+        return StepResult(next_obs=obs, next_obs_tensor=self._obs_tensor(obs), reward=0.0, done=done, info=info,
+                          selected_move=None, policy_index=0, log_prob=0.0, value_pred=0.0, success=False,
+                          error_message=message)
+
+    def execute_step(self, episode_state: EpisodeState, global_timestep: int, logger_func: Callable) -> StepResult:
+        try:
+            legal = self.game.get_legal_moves()
+            if not legal:
+                msg = (f"No legal moves available at timestep {global_timestep}. "
+                       f"Game should be in terminal state (checkmate/stalemate).")
+                logger_func(f"TERMINAL: {msg} Resetting episode.", True, None, "info")
+                return self._failure(self.game.reset(), True, {"terminal_reason": "no_legal_moves"}, msg)
+            mask = self.policy_mapper.get_legal_mask(legal, device=self.device)
+            move, policy_index, log_prob, value_pred = self.agent.select_action(episode_state.current_obs, mask,
+                                                                                is_training=True)
+            if move is None:
+                msg = f"Agent failed to select a move at timestep {global_timestep}"
+                logger_func(f"CRITICAL: {msg}. Resetting episode.", True, None, "error")
+                return self._failure(self.game.reset(), False, {}, msg)
+
+            if self.config.display.display_moves:
+                piece = None
+                try:
+                    if move[0] is not None and move[1] is not None:
+                        piece = self.game.get_piece(move[0], move[1])
+                except (AttributeError, IndexError, ValueError):
+                    pass
+                self._handle_demo_mode(move, episode_state.episode_length, piece)
+
+            mover = self.game.current_player
+            is_drop = move[0] is None and move[1] is None
+            is_promotion = isinstance(move[4], bool) and move[4]
+            result = self.game.make_move(move)
+            if not (isinstance(result, tuple) and len(result) == 4):
+                raise ValueError(f"Invalid move result: {type(result)}")
+            next_obs, reward, done, info = result
+            self._count(mover, info.get("captured_piece_type"), is_drop, is_promotion)
+            self.experience_buffer.add(episode_state.current_obs_tensor.squeeze(0), policy_index, reward, log_prob,
+                                       value_pred, done, mask)
+            return StepResult(next_obs=next_obs, next_obs_tensor=self._obs_tensor(next_obs), reward=reward, done=done,
+                              info=info, selected_move=move, policy_index=policy_index, log_prob=log_prob,
+                              value_pred=value_pred, success=True)
+        except ValueError as e:
+            msg = f"Error during training step: {e}"
+            logger_func(f"CRITICAL: {msg}. Resetting episode.", True, None, "error")
+            try:
+                return self._failure(self.game.reset(), False, {}, msg)
+            except Exception as reset_error:
+                return StepResult(next_obs=episode_state.current_obs, next_obs_tensor=episode_state.current_obs_tensor,
+                                  reward=0.0, done=True, info={}, selected_move=None, policy_index=0, log_prob=0.0,
+                                  value_pred=0.0, success=False,
+                                  error_message=f"{msg}; Reset also failed: {reset_error}")
+
+    def _count(self, mover, captured_name, is_drop: bool, is_promotion: bool) -> None:
+        black = mover == Color.BLACK or getattr(mover, "value", mover) == 0
+        if captured_name:
+            base = captured_name.replace("PROMOTED_", "")
+            value = _CAPTURE_VALUE.get(base, 0)
+            if black:
+                self.sente_capture_count += 1
+                if value > self.sente_best_capture_value:
+                    self.sente_best_capture, self.sente_best_capture_value = base.title(), value
+            else:
+                self.gote_capture_count += 1
+                if value > self.gote_best_capture_value:
+                    self.gote_best_capture, self.gote_best_capture_value = base.title(), value
+        if is_drop:
+            if black:
+                self.sente_drop_count += 1
+            else:
+                self.gote_drop_count += 1
+        if is_promotion:
+            if black:
+                self.sente_promo_count += 1
+            else:
+                self.gote_promo_count += 1
+
+    def _handle_demo_mode(self, move, episode_length: int, piece) -> None:
+        name = getattr(getattr(piece, "type", None), "name", "piece")
+        try:
+            usi = self.policy_mapper.shogi_move_to_usi(move)
+        except Exception:
+            usi = str(move)
+        self.move_log.append(f"Move {episode_length + 1}: {usi} ({name})")
+        delay = getattr(self.config.display, "turn_tick", 0.0)
+        if delay and delay > 0:
+            time.sleep(delay)
+
+    def handle_episode_end(self, episode_state: EpisodeState, step_result: StepResult, game_stats: Dict[str, int],
+                           total_episodes_completed: int, logger_func: Callable[..., None]
+                           ) -> Tuple[EpisodeState, Optional[str]]:
+        winner, reason = self._determine_winner_and_reason(step_result.info)
+        stats = dict(game_stats)
+        key = {"black": "black_wins", "white": "white_wins", None: "draws"}[winner]
+        stats[key] = stats.get(key, 0) + 1
+        total = stats["black_wins"] + stats["white_wins"] + stats["draws"]
+        rate = (lambda k: stats[k] / total if total > 0 else 0.0)
+        logger_func(
+            f"Episode {total_episodes_completed + 1} finished. Length: {episode_state.episode_length}, "
+            f"Reward: {episode_state.episode_reward:.2f}. {self._format_game_outcome_message(winner, reason)}",
+            also_to_wandb=True,
+            wandb_data={"episode_reward": episode_state.episode_reward, "episode_length": episode_state.episode_length,
+                        "game_outcome": winner, "game_reason": reason, "black_wins_total": stats["black_wins"],
+                        "white_wins_total": stats["white_wins"], "draws_total": stats["draws"],
+                        "black_win_rate": rate("black_wins"), "white_win_rate": rate("white_wins"),
+                        "draw_rate": rate("draws")},
+            log_level="info")
+        try:
+            obs = self.game.reset()
+            if not isinstance(obs, np.ndarray):
+                raise RuntimeError("Game reset failed after episode end")
+            self.move_history.clear()
+            self.move_log.clear()
+            self._reset_counters()
+            return EpisodeState(obs, self._obs_tensor(obs), 0.0, 0), winner
+        except (RuntimeError, ValueError, OSError) as e:
+            logger_func(f"CRITICAL: Game reset failed after episode end: {e}", True, None, "error")
+            return episode_state, winner
+
+    @staticmethod
+    def _determine_winner_and_reason(info: Dict[str, Any]) -> Tuple[Optional[str], str]:
+        w = info.get("winner")
+        winner = w.lower() if isinstance(w, str) and w.lower() in ("black", "white") else None
+        return winner, info.get("reason", "Unknown")
+
+    @staticmethod
+    def _format_game_outcome_message(winner: Optional[str], reason: str) -> str:
+        if winner == "black":
+            return f"Sente (Black) wins by {reason}."
+        if winner == "white":
+            return f"Gote (White) wins by {reason}."
+        return f"Draw by {reason}."
+
+    def reset_episode(self) -> EpisodeState:
+        obs = self.game.reset()
+        self.move_history.clear()
+        self.move_log.clear()
+        self._reset_counters()
+        return EpisodeState(obs, self._obs_tensor(obs), 0.0, 0)
+
+    def update_episode_state(self, episode_state: EpisodeState, step_result: StepResult) -> EpisodeState:
+        return EpisodeState(step_result.next_obs, step_result.next_obs_tensor,
+                            episode_state.episode_reward + step_result.reward, episode_state.episode_length + 1)
+
+
+class VecStepManager:
+    """Batched rollout driver: for t in [0, T): obs[t], masks[t] -> agent.select_actions -> kz_step, which writes
+    reward/done and the next observation/mask straight into obs[t+1] / masks[t+1] of the RolloutBuffer.  The
+    stored transition is the reference's (obs before the move, action, reward to the mover, log-prob, value,
+    done, mask before the move; step_manager.py:272-301); finished games are reset inside the same launch and
+    both colours' plies share one sequence per env, with no sign flips."""
+
+    def __init__(self, env, agent, buffer):
+        self.env, self.agent, self.buffer = env, agent, buffer
+        assert buffer.N == env.n
+        self.episodes = 0
+        self.black_wins = self.white_wins = self.draws = 0
+        self._started = False
+        self._stat = torch.zeros(4, dtype=torch.int64, device=env.device)
+
+    def start(self) -> None:
+        self.env.reset(refresh=False)
+        self.env.refresh(obs=self.buffer.obs[0], mask=self.buffer.masks[0])
+        self._started = True
+
+    def collect(self) -> None:
+        """Fill the buffer with T steps of N games.  No host synchronisation inside the loop."""
+        if not self._started:
+            self.start()
+        b, env = self.buffer, self.env
+        for t in range(b.T):
+            action, log_prob, value = self.agent.select_actions(b.obs[t], b.masks[t], is_training=True)
+            b.actions[t].copy_(action)
+            b.log_probs[t].copy_(log_prob)
+            b.values[t].copy_(value)
+            out = env.step(b.actions[t], obs=b.obs[t + 1], mask=b.masks[t + 1])
+            b.rewards[t].copy_(out["reward"])
+            b.dones[t].copy_(out["done"])
+            w = out["winner"]
+            d = out["done"] != 0
+            self._stat += torch.stack([d.sum(), (d & (w == 0)).sum(), (d & (w == 1)).sum(), (d & (w < 0)).sum()])
+
+    def finish(self) -> Dict[str, int]:
+        """Bootstrap values for the last observations, GAE; returns episode statistics (one host sync)."""
+        b = self.buffer
+        last_values = self.agent.get_values(b.obs[b.T])
+        b.compute_advantages_and_returns(last_values)
+        s = self._stat.tolist()
+        self._stat.zero_()
+        self.episodes += s[0]; self.black_wins += s[1]; self.white_wins += s[2]; self.draws += s[3]
+        return {"episodes": s[0], "black_wins": s[1], "white_wins": s[2], "draws": s[3]}

@@ -80,7 +80,7 @@ class VecShogiEnv:
 
     def refresh(self, obs: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
                 eval_termination: bool = False, random_actions: bool = False,
-                next_out: Optional[torch.Tensor] = None):
+                next_out: Optional[torch.Tensor] = None, in_check: Optional[torch.Tensor] = None):
         """Recompute obs / mask / legal_count (and optionally uniform-random legal actions) in place."""
         obs = self.obs if obs is None else obs
         mask = self.mask if mask is None else mask
@@ -89,7 +89,8 @@ class VecShogiEnv:
         nv.check(self._L.kz_refresh(self.state.data_ptr(), self.n, self.hist_cap, op, os_, mp, ms,
                                     self.legal_count.data_ptr(),
                                     (self.next_actions if next_out is None else next_out).data_ptr() if random_actions else None,
-                                    1, self.seed, self.step_index, self.env_offset, int(eval_termination), self._sp()),
+                                    1, self.seed, self.step_index, self.env_offset, int(eval_termination),
+                                    nv.ptr(in_check), self._sp()),
                  "kz_refresh")
         return obs, mask
 
@@ -151,4 +152,12 @@ class VecShogiEnv:
         out = torch.empty(self.n, dtype=torch.int32, device=self.device)
         nv.check(self._L.kz_errors(self.state.data_ptr(), self.n, self.hist_cap, out.data_ptr(), int(clear), self._sp()),
                  "kz_errors")
+        return out
+
+    def piece_targets(self, squares) -> torch.Tensor:
+        """Pseudo-legal target sets (81-bit, 3 x uint32 per env) of the pieces on ``squares`` [n]."""
+        sq = torch.as_tensor(np.ascontiguousarray(squares), dtype=torch.int32).to(self.device).contiguous()
+        out = torch.zeros((self.n, 3), dtype=torch.int32, device=self.device)
+        nv.check(self._L.kz_piece_targets(self.state.data_ptr(), self.n, self.hist_cap, sq.data_ptr(), out.data_ptr(),
+                                          self._sp()), "kz_piece_targets")
         return out

@@ -1,0 +1,208 @@
+"""GPU tests of the reference-API mirror: ShogiGame facade, PolicyOutputMapper, ExperienceBuffer, PPOAgent,
+EnvManager / StepManager with real objects, and the batched rollout + PPO update."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as orc  # noqa: E402  (checker only)
+from tests.helpers import make_config  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def kats(golden_dir):
+    with np.load(os.path.join(golden_dir, "kat_positions.npz")) as zf:
+        return {k: zf[k] for k in zf.files}
+
+
+def test_facade_known_answers(kats):
+    from shogidrl_b200.shogi import Color, ShogiGame
+    from shogidrl_b200.utils import PolicyOutputMapper
+    mapper = PolicyOutputMapper()
+    reasons = {0: None, 1: "Tsumi", 2: "stalemate", 3: "Max moves reached", 4: "Sennichite"}
+    for i, sfen in enumerate(kats["sfens"]):
+        g = ShogiGame.from_sfen(str(sfen))
+        assert g.game_over == bool(kats["game_over"][i]), sfen
+        assert (g.winner.value if g.winner else -1) == int(kats["winner"][i]), sfen
+        assert g.termination_reason == reasons[int(kats["reason"][i])], sfen
+        assert np.array_equal(g.get_observation(), kats["obs"][i]), sfen
+        assert [g.is_in_check(Color.BLACK), g.is_in_check(Color.WHITE)] == [bool(x) for x in kats["in_check"][i]], sfen
+        want = kats["legal"][kats["legal_off"][i]:kats["legal_off"][i + 1]].astype(np.int64)
+        moves = g.get_legal_moves()
+        got = np.sort([mapper.shogi_move_to_policy_index(m) for m in moves])
+        assert np.array_equal(got, want), sfen
+        out = g.to_sfen_string()  # hands are emitted in the reference's R,B,G,S,N,L,P order
+        assert out.split()[0] == str(sfen).split()[0] and out.split()[1] == str(sfen).split()[1], sfen
+        assert orc.parse_sfen(out)[1].tolist() == orc.parse_sfen(str(sfen))[1].tolist(), sfen
+    # reference test-suite counts
+    assert len(ShogiGame().get_legal_moves()) == 30
+    g = ShogiGame.from_sfen("9/9/9/9/4K4/9/9/9/4k4 b P 1")
+    assert len(g.get_legal_moves()) == 78
+    assert ShogiGame.from_sfen("P8/9/9/9/4k4/9/9/9/4K4 b P 1").is_nifu(Color.BLACK, 0)
+
+
+def test_facade_replays_reference_game(golden_dir):
+    """One golden game of the Python reference through the scalar API: make_move 4-tuples, boards, hands."""
+    from shogidrl_b200.shogi import ShogiGame
+    from shogidrl_b200.utils import PolicyOutputMapper
+    with np.load(os.path.join(golden_dir, "traces_random.npz")) as zf:
+        z = {k: zf[k] for k in zf.files}
+    mapper = PolicyOutputMapper()
+    gi = int(np.argmax(z["max_moves"] == 60))
+    base = int(np.sum(z["T"][:gi]))
+    g = ShogiGame(max_moves_per_game=60)
+    names = {0: "Game ongoing", 1: "Tsumi", 2: "stalemate", 3: "Max moves reached", 4: "Sennichite"}
+    for t in range(150):
+        i = base + t
+        want = z["legal"][z["legal_off"][i]:z["legal_off"][i + 1]].astype(np.int64)
+        got = np.sort([mapper.shogi_move_to_policy_index(m) for m in g.get_legal_moves()])
+        assert np.array_equal(got, want), t
+        obs, reward, done, info = g.make_move(mapper.policy_index_to_shogi_move(int(z["actions"][i])))
+        assert obs.shape == (46, 9, 9) and obs.dtype == np.float32
+        assert reward == float(z["rewards"][i]) and done == bool(z["dones"][i]) and info["reason"] == names[int(z["reasons"][i])]
+        b = np.array([[0 if p is None else p.code for p in row] for row in g.board], np.int8).reshape(81)
+        assert np.array_equal(b, z["boards"][i]), t
+        assert g.move_count == int(z["move_counts"][i]) and g.current_player.value == int(z["sides"][i])
+        if done:
+            assert ("winner" in info) == (int(z["winners"][i]) >= 0)
+            again = g.make_move((0, 0, 1, 0, False))  # finished game: the terminal tuple again (shogi_game.py:589-593)
+            assert again[2] is True and again[3]["reason"] == info["reason"]
+            g.reset()
+
+
+def test_facade_errors_undo_sennichite_deepcopy():
+    from shogidrl_b200.shogi import Color, Piece, PieceType, ShogiGame
+    g = ShogiGame()
+    with pytest.raises(ValueError, match="Illegal movement pattern"):
+        g.make_move((6, 0, 4, 0, False))
+    with pytest.raises(ValueError, match="Invalid move_tuple format"):
+        g.make_move((6, 0, 5, 0))
+    with pytest.raises(ValueError, match="No piece at source"):
+        g.make_move((4, 4, 3, 4, False))
+    sfen0 = g.to_sfen_string()
+    g.make_move((6, 6, 5, 6, False))
+    assert g.current_player == Color.WHITE and g.move_count == 1 and len(g.move_history) == 1
+    g.undo_move()
+    assert g.to_sfen_string() == sfen0 and g.move_history == []
+    assert sorted(g.get_individual_piece_moves(Piece(PieceType.ROOK, Color.BLACK), 4, 4)) == sorted(
+        [(r, 4) for r in (3, 5)] + [(4, c) for c in range(9) if c != 4] + [(2, 4), (6 - 0, 4)][:1])
+    assert g.test_move((6, 6, 5, 6, False)) and not g.test_move((6, 6, 4, 6, False))
+    # sennichite on the 13th ply of a 4-ply cycle (tests/shogi/test_shogi_game_core_logic.py:1126-1179)
+    g = ShogiGame.from_sfen("4k4/9/9/9/9/R8/9/9/4K4 b - 1")
+    cycle = [(5, 0, 5, 1, False), (0, 4, 0, 3, False), (5, 1, 5, 0, False), (0, 3, 0, 4, False)]
+    for i in range(12):
+        _, _, done, _ = g.make_move(cycle[i % 4])
+        assert not done, i
+    _, r, done, info = g.make_move(cycle[0])
+    assert done and info["reason"] == "Sennichite" and r == 0.0 and g.is_sennichite()
+    g2 = copy.deepcopy(ShogiGame())
+    assert g2.move_history == [] and len(g2.board_history) == 1
+    # max moves through the private attribute the reference's tests poke
+    g = ShogiGame()
+    g._max_moves_this_game = 2
+    g.make_move((6, 6, 5, 6, False))
+    _, _, done, info = g.make_move((2, 2, 3, 2, False))
+    assert done and info["reason"] == "Max moves reached"
+    # get_legal_moves on a finished game clears the flags, as the reference's simulation undo does
+    g = ShogiGame.from_sfen("9/9/9/9/9/4G4/4r4/4g4/4K4 b - 1")
+    assert g.game_over and g.get_legal_moves() == [] and not g.game_over
+
+
+def test_experience_buffer_gae_known_answer():
+    from shogidrl_b200.core import ExperienceBuffer
+    buf = ExperienceBuffer(3, 0.99, 0.95, "cuda")
+    o, m = torch.zeros(46, 9, 9), torch.zeros(13527, dtype=torch.bool)
+    for r, v, d in [(1.0, 0.5, False), (2.0, 1.0, False), (3.0, 1.5, True)]:
+        buf.add(o, 0, r, 0.0, v, d, m)
+    buf.compute_advantages_and_returns(2.0)
+    batch = buf.get_batch()
+    assert float(batch["advantages"][2]) == 1.5 and float(batch["returns"][2]) == 3.0  # tests/conftest.py:543-581
+    a, r = orc.gae_numpy(np.array([[1.], [2.], [3.]], np.float32), np.array([[.5], [1.], [1.5]], np.float32),
+                         np.array([[0], [0], [1]]), np.array([2.0], np.float32), 0.99, 0.95)
+    assert np.array_equal(batch["advantages"].cpu().numpy(), a[:, 0]) and np.array_equal(batch["returns"].cpu().numpy(), r[:, 0])
+
+
+def test_agent_select_action_and_step_manager_real_objects():
+    from shogidrl_b200.core import ActorCritic, ExperienceBuffer, PPOAgent
+    from shogidrl_b200.training import EnvManager, StepManager
+    cfg = make_config()
+    logs = []
+    em = EnvManager(cfg, logs.append)
+    game, mapper = em.setup_environment()
+    assert em.validate_environment() and em.get_legal_moves_count() == 30
+    torch.manual_seed(0)
+    agent = PPOAgent(ActorCritic(46, 13527), cfg, torch.device("cuda"))
+    buf = ExperienceBuffer(64, cfg.training.gamma, cfg.training.lambda_gae, "cuda")
+    sm = StepManager(cfg, game, agent, mapper, buf)
+    st = sm.reset_episode()
+    mask = mapper.get_legal_mask(game.get_legal_moves(), torch.device("cuda"))
+    move, idx, lp, v = agent.select_action(st.current_obs, mask, is_training=True)
+    assert bool(mask[idx]) and np.isfinite(lp) and np.isfinite(v) and move == mapper.policy_index_to_shogi_move(idx)
+    single = torch.zeros(13527, dtype=torch.bool, device="cuda"); single[1234] = True
+    assert agent.select_action(st.current_obs, single, is_training=True)[1] == 1234
+    assert agent.select_action(st.current_obs, mask, is_training=False)[1] == agent.select_action(st.current_obs, mask, is_training=False)[1]
+    assert np.isfinite(agent.get_value(st.current_obs))
+    log = lambda *a, **k: None
+    for t in range(64):
+        res = sm.execute_step(st, t, log)
+        assert res.success
+        st = sm.update_episode_state(st, res)
+        if res.done:
+            st, _ = sm.handle_episode_end(st, res, {"black_wins": 0, "white_wins": 0, "draws": 0}, 0, log)
+    assert len(buf) == 64
+    buf.compute_advantages_and_returns(agent.get_value(st.current_obs))
+    metrics = agent.learn(buf)
+    assert all(np.isfinite(x) for x in metrics.values()) and "ppo/clip_fraction" in metrics
+    # every stored mask row has the chosen action legal
+    b = buf.get_batch()
+    assert bool(b["legal_masks"].gather(1, b["actions"][:, None]).all())
+
+
+def test_vectorised_rollout_and_update():
+    from shogidrl_b200 import VecShogiEnv
+    from shogidrl_b200.core import ActorCritic, PPOAgent, RolloutBuffer
+    from shogidrl_b200.training import VecStepManager
+    cfg = make_config(minibatch_size=256, ppo_epochs=1)
+    dev = torch.device("cuda")
+    N, T = 256, 16
+    env = VecShogiEnv(N, max_moves_per_game=40, device=dev, seed=5)
+    torch.manual_seed(1)
+    agent = PPOAgent(ActorCritic(46, 13527), cfg, dev, use_mixed_precision=True)
+    buf = RolloutBuffer(T, N, 0.99, 0.95, dev)
+    drv = VecStepManager(env, agent, buf)
+    total_eps = 0
+    for _ in range(4):
+        drv.collect()
+        stats = drv.finish()
+        total_eps += stats["episodes"]
+        b = buf.get_batch()
+        assert b["obs"].shape == (T * N, 46, 9, 9) and b["legal_masks"].dtype == torch.bool
+        assert bool(b["legal_masks"].gather(1, b["actions"][:, None]).all())
+        # stored observations are the engine's observation of the stored state: plane 42 = side to move
+        assert bool(((b["obs"][:, 42, 0, 0] == 0) | (b["obs"][:, 42, 0, 0] == 1)).all())
+        a_ref, r_ref = orc.gae(buf.rewards.cpu().numpy(), buf.values.cpu().numpy(), buf.dones.cpu().numpy(),
+                               agent.get_values(buf.obs[T]).cpu().numpy(), 0.99, 0.95)
+        assert np.allclose(buf.advantages.cpu().numpy(), a_ref, rtol=1e-5, atol=1e-6)
+        m = agent.learn(buf)
+        assert all(np.isfinite(x) for x in m.values())
+        buf.clear()
+    assert total_eps > 0 and drv.black_wins + drv.white_wins + drv.draws == drv.episodes
+    assert int(env.errors().abs().sum()) == 0
+
+
+def test_parallel_manager_shim():
+    from shogidrl_b200.core import ActorCritic, ExperienceBuffer, PPOAgent
+    from shogidrl_b200.training.parallel import ParallelManager
+    cfg = make_config()
+    agent = PPOAgent(ActorCritic(46, 13527), cfg, torch.device("cuda"))
+    pm = ParallelManager({"max_moves_per_game": 500, "seed": 3}, {}, {"num_workers": 8, "batch_size": 4}, "cuda")
+    assert pm.start_workers(agent) and pm.is_healthy()
+    buf = ExperienceBuffer(100, 0.99, 0.95, "cuda")
+    assert pm.collect_experiences(buf) == 32 and pm.collect_experiences(buf) == 32 and len(buf) == 64
+    assert bool(buf.legal_masks[:64].gather(1, buf.actions[:64, None]).all())
+    pm.stop_workers()
+    assert not pm.is_healthy() and pm.get_parallel_stats()["total_steps_collected"] == 64
