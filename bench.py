@@ -313,6 +313,77 @@ def run_product(args):
     return 0
 
 
+def run_ppo(args):
+    """--workload ppo: BASELINE config 3 -- PPO self-play with the default CNN policy-value net (bf16 autocast),
+    16,384 envs, rollout T = 128, fused masked sampling, device GAE, then the PPO update.  One step = one full
+    epoch (collect + update); value = samples (env steps) per second end to end; rollout-only rate in config."""
+    import torch
+    import torch.distributed as dist
+    from types import SimpleNamespace
+    from shogidrl_b200.core import ActorCritic, ActorCriticResTower
+    from shogidrl_b200.training.selfplay import SelfPlayTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N, T = args.ppo_envs, args.ppo_horizon
+    mb = args.ppo_minibatch
+    cfg = SimpleNamespace(
+        env=SimpleNamespace(device=str(dev), seed=SEED, input_channels=46, num_actions_total=13527, max_moves_per_game=MAX_MOVES),
+        training=SimpleNamespace(learning_rate=3e-4, gamma=0.99, lambda_gae=0.95, clip_epsilon=0.2, value_loss_coeff=0.5,
+                                 entropy_coef=0.01, ppo_epochs=args.ppo_epochs, minibatch_size=mb, steps_per_epoch=N * T,
+                                 total_timesteps=N * T * 8, gradient_clip_max_norm=0.5, normalize_advantages=True,
+                                 enable_value_clipping=False, weight_decay=0.0, lr_schedule_type=None,
+                                 lr_schedule_step_on="epoch", lr_schedule_kwargs=None),
+        display=SimpleNamespace(display_moves=False, turn_tick=0.0))
+    torch.manual_seed(SEED + rank)
+    if args.ppo_model == "resnet":
+        model = ActorCriticResTower(46, 13527, tower_depth=9, tower_width=256, se_ratio=0.25)
+    else:
+        model = ActorCritic(46, 13527)
+    tr = SelfPlayTrainer(model, cfg, N, T, dev, use_mixed_precision=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(1, args.warmup if args.warmup < 3 else 1)):
+        tr.run_epoch()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    roll_ms = upd_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ev[0].record(); tr.collect(); ev[1].record(); m = tr.update(); ev[2].record()
+        torch.cuda.synchronize(dev)
+        roll_ms += ev[0].elapsed_time(ev[1]); upd_ms += ev[1].elapsed_time(ev[2])
+    barrier()
+    total_ms = 1e3 * (time.perf_counter() - t0)
+    if world > 1:
+        t = torch.tensor([total_ms, roll_ms, upd_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, roll_ms, upd_ms = [float(x) for x in t]
+    if rank == 0:
+        samples = world * N * T * args.steps
+        line = {"metric": "PPO self-play samples/sec", "value": samples / (total_ms * 1e-3), "unit": "samples/s",
+                "n_gpus": world, "steps": args.steps, "warmup": 1, "ms_per_step": total_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"BASELINE config 3: PPO self-play, {args.ppo_model} policy-value net (bf16 autocast), {N} envs/GPU, "
+                                       f"T={T}, fused masked sampling + device GAE, ppo_epochs={args.ppo_epochs}, minibatch={mb}",
+                           "rollout_samples_per_s": samples / (roll_ms * 1e-3), "update_samples_per_s": samples / (upd_ms * 1e-3),
+                           "rollout_ms": roll_ms / args.steps, "update_ms": upd_ms / args.steps,
+                           "last_metrics": {k: float(v) for k, v in m.items()}},
+                "gpu_launches": args.steps * T}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -322,6 +393,12 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="games per GPU (BASELINE config 2: 65,536)")
     ap.add_argument("--preroll", type=int, default=PREROLL)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="env", choices=["env", "ppo"], help="env: BASELINE config 2 (default, the headline); ppo: config 3")
+    ap.add_argument("--ppo-envs", type=int, default=16384)
+    ap.add_argument("--ppo-horizon", type=int, default=128)
+    ap.add_argument("--ppo-epochs", type=int, default=10)
+    ap.add_argument("--ppo-minibatch", type=int, default=16384)
+    ap.add_argument("--ppo-model", default="cnn", choices=["cnn", "resnet"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -332,6 +409,8 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    if args.workload == "ppo":
+        return run_ppo(args)
     return run_product(args)
 
 
