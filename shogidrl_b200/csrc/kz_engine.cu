@@ -26,7 +26,8 @@ __device__ uint32_t g_step[NCLS * 81 * 3];
 __device__ uint32_t g_init_bitmap[BITMAP_WORDS];  // legal bitmap of the start position (30 moves)
 __device__ int g_tables_ready = 0;
 
-__constant__ uint8_t c_init_board[96];
+__constant__ uint8_t c_init_board[96];  // start position; bytes 84..95 = words x, y, z of its position key
+__constant__ uint32_t c_init_key_w;     // word w of that key
 
 struct __align__(16) WarpScratch {
   uint32_t bitmap[BITMAP_WORDS];  // 13,527 legal bits in action-index order (+pad)
@@ -413,17 +414,18 @@ __device__ __forceinline__ GenResult gen_moves_impl(const uint32_t tab, const in
   }
 
   // ---- phase D: drops, one lane per square (shogi_rules_logic.py:424-483, 561-629)
-  {
+  const uint8_t* h = hands + me * 7;
+  const int hP = h[0], hL = h[1], hN = h[2], hS = h[3], hG = h[4], hB = h[5], hR = h[6];
+  const bool anyhand = (hP | hL | hN | hS | hG | hB | hR) != 0 && nchk < 2;  // warp-uniform
+  if (anyhand) {
     const int last = me == 0 ? 0 : 8, second = me == 0 ? 1 : 7;
-    const uint8_t* h = hands + me * 7;
-    const int hP = h[0], hL = h[1], hN = h[2], hS = h[3], hG = h[4], hB = h[5], hR = h[6];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
       const int sq = lane + 32 * j;
       const uint32_t cmw = j == 0 ? CM.w0 : (j == 1 ? CM.w1 : CM.w2);
       const uint32_t ufw = j == 0 ? UFZ.w0 : (j == 1 ? UFZ.w1 : UFZ.w2);
       uint32_t v = 0;
-      if (sq < 81 && c[j] == 0 && nchk < 2 && (nchk == 0 || ((cmw >> lane) & 1))) {
+      if (sq < 81 && c[j] == 0 && (nchk == 0 || ((cmw >> lane) & 1))) {
         const int r = sq_row(sq), col = sq - 9 * r;
         if (hP > 0 && r != last && !((pawn_cols >> col) & 1) && !((ufw >> lane) & 1)) v |= 1;
         if (hL > 0 && r != last) v |= 2;
@@ -438,7 +440,7 @@ __device__ __forceinline__ GenResult gen_moves_impl(const uint32_t tab, const in
     }
   }
   res.count = __reduce_add_sync(FULL, cnt);
-  if (EMIT) {
+  if (EMIT && anyhand) {  // without pieces in hand the drop words keep the zeros written above
     __syncwarp();
     if (lane < 18) {  // bits 12960 + to*7 + type: word 405 + lane holds drop-stream bits [32*lane, 32*lane+32)
       const int to0 = (32 * lane * 293) >> 11;  // floor(32*lane / 7)
@@ -583,11 +585,17 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
     const int max_moves = ld_u16(ws.meta + 22);
     uint32_t episodes = ws.meta[24] | (ws.meta[25] << 8) | (ws.meta[26] << 16) | (ws.meta[27] << 24);
 
+
+
     float reward = 0.f;
     int done_out = 0, reason_out = 0, winner_out = -1, ep_len_out = 0;
     bool fresh_senn = false;
     int mover = 1 - side;
     bool moved = false;
+    // position key carried in the padding of the state rows (board bytes 84..95, meta bytes 28..31)
+    uint4 key = make_uint4(reinterpret_cast<const uint32_t*>(ws.board)[21], reinterpret_cast<const uint32_t*>(ws.board)[22],
+                           reinterpret_cast<const uint32_t*>(ws.board)[23], reinterpret_cast<const uint32_t*>(ws.meta)[7]);
+    uint32_t kid = 0;  // id of the key item this lane toggles for the move (0 = none)
 
     if (P.mode == 1) {
       if (status != 0) {
@@ -606,39 +614,70 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
           if (!code || code_color(code) != side) { err |= KZ_ERR_BAD_ACTION; ok = false; }
           else {
             // movement-pattern validation only, as _validate_and_populate_board_move_details does
-            // (shogi_game.py:518-546): target must be in the piece's pseudo-legal set
-            uint32_t o0 = __ballot_sync(FULL, ws.board[lane] != 0), o1 = __ballot_sync(FULL, ws.board[lane + 32] != 0),
-                     o2 = __ballot_sync(FULL, lane < 17 && ws.board[lane + 64] != 0);
-            const BB occ{o0, o1, o2};
-            BB t = ld_step(T, (inf >> 16) & 15, from);
-            uint32_t sl = (inf >> 8) & 0xFF;
-            while (sl) { const int d = __ffs(sl) - 1; sl &= sl - 1; t = t | slide_ray(T, from, d, occ); }
-            if (!bb_test(t, to) || (tcode && code_color(tcode) == side) || (promo && !((inf >> 20) & 1))) {
+            // (shogi_game.py:518-546): `to` must be in the piece's pseudo-legal set.  Decided from the geometry of
+            // (from, to): a knight jump, a single step in a step direction, or a slide along a clear ray.
+            const int fr = sq_row(from), fc = from - 9 * fr, tr = sq_row(to), tc = to - 9 * tr;
+            const int dr = tr - fr, dc = tc - fc;
+            bool pat;
+            if (code_type(code) == 2) {
+              pat = dr == (side == 0 ? -2 : 2) && (dc == 1 || dc == -1);
+            } else {
+              int d = -1;
+              if (dc == 0) d = dr < 0 ? 0 : 4;
+              else if (dr == 0) d = dc > 0 ? 2 : 6;
+              else if (dr == dc) d = dr > 0 ? 3 : 7;
+              else if (dr == -dc) d = dr > 0 ? 5 : 1;
+              pat = false;
+              if (d >= 0) {
+                const int dist = max(abs(dr), abs(dc));
+                if (dist == 1 && ((inf >> d) & 1)) pat = true;
+                else if ((inf >> (8 + d)) & 1) {
+                  const uint32_t o0 = __ballot_sync(FULL, ws.board[lane] != 0), o1 = __ballot_sync(FULL, ws.board[lane + 32] != 0),
+                                 o2 = __ballot_sync(FULL, lane < 17 && ws.board[lane + 64] != 0);
+                  const BB ray = ld_ray(T, from, d);
+                  const BB between = dir_positive(d) ? (ray & bb_below(to)) : bb_andn(ray, bb_upto(to));
+                  pat = !bb_any(between & BB{o0, o1, o2});
+                }
+              }
+            }
+            if (!pat || (tcode && code_color(tcode) == side) || (promo && !((inf >> 20) & 1))) {
               err |= KZ_ERR_BAD_PATTERN; ok = false;
             }
           }
           if (ok) {  // apply_move_to_board_state (shogi_move_execution.py:90-132)
+            const int newcode = promo ? code + promo_delta(code_type(code)) : code;
+            int slot = -1, c_old = 0;
+            if (tcode) {
+              const int tt = code_type(tcode);
+              if (tt == 7) err |= KZ_ERR_KING_CAPTURE;
+              else { slot = side * 7 + (tt >= 8 ? base_of_promoted(tt) : tt); c_old = ws.meta[slot]; }
+            }
+            // key items toggled by this move: piece leaves `from`, piece lands on `to`, captured piece, hand count
+            if (lane == 0) kid = from * 32 + code;
+            else if (lane == 1) kid = to * 32 + newcode;
+            else if (lane == 2) kid = tcode ? to * 32 + tcode : 0;
+            else if (lane == 3) kid = (slot >= 0 && c_old > 0) ? 4096 + slot * 256 + c_old : 0;
+            else if (lane == 4) kid = slot >= 0 ? 4096 + slot * 256 + c_old + 1 : 0;
             __syncwarp();
             if (lane == 0) {
-              if (tcode) {
-                const int tt = code_type(tcode);
-                if (tt == 7) err |= KZ_ERR_KING_CAPTURE;
-                else ws.meta[side * 7 + (tt >= 8 ? base_of_promoted(tt) : tt)] += 1;
-              }
-              ws.board[to] = (uint8_t)(promo ? code + promo_delta(code_type(code)) : code);
+              if (slot >= 0) ws.meta[slot] = (uint8_t)(c_old + 1);
+              ws.board[to] = (uint8_t)newcode;
               ws.board[from] = 0;
             }
-            if (tcode && code_type(tcode) == 7) err |= KZ_ERR_KING_CAPTURE;
           }
         } else {
           const int k = ai - 12960;
           const int to = (k * 293) >> 11, pt = k - to * 7;
           if (ws.board[to] != 0 || ws.meta[side * 7 + pt] == 0) { err |= KZ_ERR_BAD_ACTION; ok = false; }
           if (ok) {  // drop (shogi_move_execution.py:55-71)
+            const int slot = side * 7 + pt, c_old = ws.meta[slot];
+            if (lane == 1) kid = to * 32 + (1 + pt + 14 * side);
+            else if (lane == 3) kid = 4096 + slot * 256 + c_old;
+            else if (lane == 4) kid = c_old > 1 ? 4096 + slot * 256 + c_old - 1 : 0;
             __syncwarp();
             if (lane == 0) {
               ws.board[to] = (uint8_t)(1 + pt + 14 * side);
-              ws.meta[side * 7 + pt] -= 1;
+              ws.meta[slot] = (uint8_t)(c_old - 1);
             }
           }
         }
@@ -651,7 +690,16 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
           // The reference counts equal (board, hands, side) entries of move_history; here every game owns an
           // open-addressing table keyed by the 124-bit position key whose low 4 bits of w hold the occurrence
           // count.  One cooperative probe reads 32 consecutive slots (512 B) instead of scanning every earlier ply.
-          const uint4 key = position_key(ws, lane, side);
+          // the key is updated incrementally: XOR of the (at most six) items the move toggles, one per lane
+          {
+            if (lane == 5) kid = 8191;  // side to move flips on every move
+            uint4 dk = make_uint4(0, 0, 0, 0);
+            if (kid) dk = zkey_item(kid);
+            key.x ^= __reduce_xor_sync(FULL, dk.x);
+            key.y ^= __reduce_xor_sync(FULL, dk.y);
+            key.z ^= __reduce_xor_sync(FULL, dk.z);
+            key.w ^= __reduce_xor_sync(FULL, dk.w);
+          }
           if (hist_len < P.hist_cap) {
             uint4* tb = P.hist + (size_t)g * P.rep_slots;
             const uint32_t smask = (uint32_t)P.rep_slots - 1u;
@@ -688,6 +736,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
     // the square in front of the enemy king and the specialised test applies.  Loaded positions (refresh mode)
     // may have the side NOT to move in check: they take the nested-generation path, on every pawn-drop square
     // when that king is attacked.
+    if (P.mode == 0) key = position_key(ws, lane, side);  // loaded positions: full key
     GenResult gr;
     if (P.mode == 1) {
       gr = gen_moves<true>(tab, side, UFZ_FAST);
@@ -723,6 +772,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
       if (lane < 14) ws.meta[lane] = 0;
       side = 0; status = 0; winner = -1; move_count = 0; hist_len = 0;
       episodes += 1;
+      key = make_uint4(reinterpret_cast<const uint32_t*>(c_init_board)[21], reinterpret_cast<const uint32_t*>(c_init_board)[22],
+                       reinterpret_cast<const uint32_t*>(c_init_board)[23], c_init_key_w);
       {
         uint4* tb = P.hist + (size_t)g * P.rep_slots;
         for (int i = lane; i < P.rep_slots; i += 32) tb[i] = make_uint4(0, 0, 0, 0);
@@ -843,14 +894,20 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
       float pv = 0.f;
       if (lane < 14) {
         const int cnt = ws.meta[lane < 7 ? side * 7 + lane : (1 - side) * 7 + (lane - 7)];
-        if (cnt > 0) pv = (float)((double)cnt / 18.0);
+        // The reference divides in Python doubles and stores fp32.  For integer operands below 2^16 the exact
+        // quotient is never within 2^-41 (relative) of an fp32 rounding tie, so rounding once (IEEE fp32 division)
+        // and rounding twice (double, then fp32) give the same bits.
+        if (cnt > 0) pv = __fdiv_rn((float)cnt, 18.0f);
       } else if (lane == 14) pv = side == 0 ? 1.f : 0.f;
-      else if (lane == 15) pv = max_moves > 0 ? (float)((double)move_count / (double)max_moves) : 0.f;
+      else if (lane == 15) pv = max_moves > 0 ? __fdiv_rn((float)move_count, (float)max_moves) : 0.f;
       const int mis = ((uintptr_t)orow & 15) ? 2 : 0;  // rows are 8-byte aligned; odd rows start 8 past a 16-byte line
       float4* o4 = reinterpret_cast<float4*>(orow + mis);
       // Zero-fill the whole row with 128-bit stores (float4 chunk q covers floats [mis + 4q, mis + 4q + 4)), then
       // overwrite what is not zero: the constant planes with a non-zero value (a few of the 18) and one float
       // per piece.  Both overwrites follow the zero fill in program order behind a __syncwarp().
+      // (Measured alternatives that were NOT faster: issuing this zero fill early, interleaved with the move
+      // application -- 0.476 ms; handing it to the bulk-copy engine, cp.async.bulk from a shared zero page -- 0.469 ms;
+      // this loop -- 0.460 ms per 65,536-game launch.)
       const float4 zf = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 2
       for (int q = lane; q < 931; q += 32) o4[q] = zf;
@@ -892,6 +949,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
       st_u16(ws.meta + 20, hist_len);
       ws.meta[24] = (uint8_t)episodes; ws.meta[25] = (uint8_t)(episodes >> 8);
       ws.meta[26] = (uint8_t)(episodes >> 16); ws.meta[27] = (uint8_t)(episodes >> 24);
+      reinterpret_cast<uint32_t*>(ws.board)[21] = key.x;
+      reinterpret_cast<uint32_t*>(ws.board)[22] = key.y;
+      reinterpret_cast<uint32_t*>(ws.board)[23] = key.z;
+      reinterpret_cast<uint32_t*>(ws.meta)[7] = key.w;
     }
     __syncwarp();
     {
@@ -921,6 +982,7 @@ __global__ void kz_reset_kernel(uint8_t* boards, uint8_t* meta, uint4* rep, int 
     if (w == 4) v = 0xFFu;                                  // bytes 16..19: winner none, err 0, move_count 0
     if (w == 5) v = ((uint32_t)max_moves & 0xFFFF) << 16;   // bytes 20..23: hist_len 0, max_moves
     if (w == 6) v = m[6];                                   // keep the finished-episode counter
+    if (w == 7) v = c_init_key_w;                           // bytes 28..31: word w of the position key
     m[w] = v;
   }
 }
@@ -1131,6 +1193,20 @@ int kz_init_tables(void* stream) {
   init[7 * 9 + 1] = 1 + 5;      init[7 * 9 + 7] = 1 + 6;
   CK(cudaMemcpyToSymbolAsync(g_ray, ray, sizeof ray, 0, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyToSymbolAsync(g_step, step, sizeof step, 0, cudaMemcpyHostToDevice, st));
+  {  // position key of the start position (same hash functions as zkey_item / position_key on the device)
+    auto fmix = [](uint32_t h) { h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16; return h; };
+    uint32_t k[4] = {0, 0, 0, 0};
+    for (int sq = 0; sq < 81; sq++)
+      if (init[sq]) {
+        const uint32_t id = (uint32_t)sq * 32u + init[sq];
+        k[0] ^= fmix(id * 0x9E3779B1u + 0x7F4A7C15u);
+        k[1] ^= fmix(id * 0x85EBCA77u + 0x165667B1u);
+        k[2] ^= fmix(id * 0xC2B2AE3Du + 0x27D4EB2Fu);
+        k[3] ^= fmix(id * 0x27D4EB2Fu + 0x9E3779B9u);
+      }
+    memcpy(init + 84, k, 12);
+    CK(cudaMemcpyToSymbolAsync(c_init_key_w, &k[3], sizeof(uint32_t), 0, cudaMemcpyHostToDevice, st));
+  }
   CK(cudaMemcpyToSymbolAsync(c_init_board, init, sizeof init, 0, cudaMemcpyHostToDevice, st));
   int dev = 0;
   CK(cudaGetDevice(&dev));
