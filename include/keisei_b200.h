@@ -154,6 +154,18 @@ int kz_gae(const float* rewards, const float* values, const uint8_t* dones, cons
 int kz_gae_exact(const float* rewards, const float* values, const uint8_t* dones, const float* last_value,
                  int T, int N, float gamma, float gamma_lambda, float* adv, float* ret, void* stream);
 
+/* BaseActorCriticModel.evaluate_actions after forward() (base_actor_critic.py:118-184) for the PPO update
+ * (SURVEY 8f-1): masked softmax, log-prob of the taken action and entropy (Categorical(probs) clamp semantics),
+ * forward and backward.  logits [n][ld] fp32/bf16; mask rows are mask[mask_rows[i]] when mask_rows != NULL (lets
+ * a minibatch index the rollout's mask storage without gathering it); saved4 [n][4] fp32 scratch handed from
+ * forward to backward; dlogits [n][ldg] in the logits dtype (pad columns beyond 13,527 are not written). */
+int kz_eval_masked_fwd(const void* logits, int logits_bf16, int64_t ld, const uint8_t* mask, int64_t ldm,
+                       const int64_t* mask_rows, const int64_t* actions, int n, float* logp, float* entropy,
+                       float* saved4, void* stream);
+int kz_eval_masked_bwd(const void* logits, int logits_bf16, int64_t ld, const uint8_t* mask, int64_t ldm,
+                       const int64_t* mask_rows, const int64_t* actions, int n, const float* dlogp,
+                       const float* dentropy, const float* saved4, void* dlogits, int64_t ldg, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

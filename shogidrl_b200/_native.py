@@ -21,7 +21,7 @@ REASONS = {0: None, 1: "Tsumi", 2: "stalemate", 3: "Max moves reached", 4: "Senn
 EXPORTS = [
     "kz_abi_version", "kz_last_cuda_error", "kz_init_tables", "kz_state_layout", "kz_reset", "kz_load_positions",
     "kz_export_positions", "kz_piece_targets", "kz_refresh", "kz_step", "kz_legal_mask", "kz_observe", "kz_errors", "kz_sample_masked",
-    "kz_gae", "kz_gae_exact",
+    "kz_gae", "kz_gae_exact", "kz_eval_masked_fwd", "kz_eval_masked_bwd",
 ]
 
 
@@ -60,6 +60,8 @@ def lib() -> C.CDLL:
     L.kz_sample_masked.argtypes = [vp, i32, i64, vp, i64, i32, u64, u64, vp, i32, vp, vp, i32, vp]
     L.kz_gae.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp, vp]
     L.kz_gae_exact.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp, vp]
+    L.kz_eval_masked_fwd.argtypes = [vp, i32, i64, vp, i64, vp, vp, i32, vp, vp, vp, vp]
+    L.kz_eval_masked_bwd.argtypes = [vp, i32, i64, vp, i64, vp, vp, i32, vp, vp, vp, vp, i64, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("kz_last_cuda_error",):

@@ -69,8 +69,20 @@ class BaseActorCriticModel(nn.Module):
 
     @staticmethod
     def evaluate_from_logits(logits: torch.Tensor, value: torch.Tensor, actions: torch.Tensor,
-                             legal_mask: Optional[torch.Tensor] = None):
-        """log-prob / entropy / value from a forward pass that may have gone through a DDP wrapper."""
+                             legal_mask: Optional[torch.Tensor] = None, mask_rows: Optional[torch.Tensor] = None):
+        """log-prob / entropy / value from a forward pass that may have gone through a DDP wrapper.  On CUDA the
+        masked softmax, log-prob gather, entropy and their backward run in one fused kernel pair
+        (rl.evaluate_masked); ``mask_rows`` lets ``legal_mask`` be the whole rollout mask storage."""
+        if logits.is_cuda and logits.dtype in (torch.float32, torch.bfloat16):
+            if legal_mask is None:
+                legal_mask = torch.ones((logits.shape[0], logits.shape[1]), dtype=torch.uint8, device=logits.device)
+                mask_rows = None
+            log_probs, entropy = rl.evaluate_masked(logits, legal_mask, actions, mask_rows)
+            if value.dim() > 1 and value.shape[-1] == 1:
+                value = value.squeeze(-1)
+            return log_probs, entropy, value
+        if mask_rows is not None and legal_mask is not None:
+            legal_mask = legal_mask[mask_rows]
         logits = logits.float()
         if legal_mask is not None:
             logits = torch.where(legal_mask.bool(), logits, torch.full((), float("-inf"), device=logits.device))

@@ -157,7 +157,9 @@ class PPOAgent:
                 mb = torch.as_tensor(indices[start:start + self.minibatch_size], device=d)
                 with self._autocast():
                     logits, values = self._train_forward(self._scale(obs_b[mb]))
-                    new_lp, entropy, new_v = type(self.model).evaluate_from_logits(logits, values, act_b[mb], mask_b[mb])
+                    # masks are read in place from the rollout storage through the minibatch indices (no gather)
+                    new_lp, entropy, new_v = type(self.model).evaluate_from_logits(logits, values, act_b[mb], mask_b,
+                                                                                   mask_rows=mb)
                 new_v = new_v.float()
                 ratio = torch.exp(new_lp - oldlp_b[mb])
                 adv = adv_b[mb]

@@ -48,3 +48,50 @@ def gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, last_v
     nv.check(fn(r.data_ptr(), v.data_ptr(), d.data_ptr(), lv.data_ptr(), T, N, float(gamma),
                 float(gamma * lambda_gae), adv.data_ptr(), ret.data_ptr(), nv.stream_ptr(dev)), "kz_gae")
     return adv, ret
+
+
+class _MaskedCategoricalEval(torch.autograd.Function):
+    """log-prob of taken actions + entropy of the masked softmax, fused forward/backward (kz_eval_masked_*)."""
+
+    @staticmethod
+    def forward(ctx, logits, mask, actions, mask_rows):
+        dev = nv.require_cuda(logits.device)
+        n = logits.shape[0]
+        logp = torch.empty(n, dtype=torch.float32, device=dev)
+        ent = torch.empty(n, dtype=torch.float32, device=dev)
+        saved = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        actions = actions.contiguous().long()
+        nv.check(nv.lib().kz_eval_masked_fwd(logits.data_ptr(), int(logits.dtype == torch.bfloat16), logits.stride(0),
+                                             mask.data_ptr(), mask.stride(0), nv.ptr(mask_rows), actions.data_ptr(), n,
+                                             logp.data_ptr(), ent.data_ptr(), saved.data_ptr(), nv.stream_ptr(dev)),
+                 "kz_eval_masked_fwd")
+        ctx.save_for_backward(logits, mask, actions, saved)
+        ctx.mask_rows = mask_rows
+        return logp, ent
+
+    @staticmethod
+    def backward(ctx, dlogp, dent):
+        logits, mask, actions, saved = ctx.saved_tensors
+        dev = logits.device
+        n = logits.shape[0]
+        ldg = (nv.NUM_ACTIONS + 15) // 16 * 16
+        store = torch.zeros((n, ldg), dtype=logits.dtype, device=dev)  # padded rows: vector-friendly for the GEMM backward
+        nv.check(nv.lib().kz_eval_masked_bwd(logits.data_ptr(), int(logits.dtype == torch.bfloat16), logits.stride(0),
+                                             mask.data_ptr(), mask.stride(0), nv.ptr(ctx.mask_rows), actions.data_ptr(), n,
+                                             dlogp.contiguous().float().data_ptr(), dent.contiguous().float().data_ptr(),
+                                             saved.data_ptr(), store.data_ptr(), ldg, nv.stream_ptr(dev)),
+                 "kz_eval_masked_bwd")
+        return store[:, : nv.NUM_ACTIONS], None, None, None
+
+
+def evaluate_masked(logits: torch.Tensor, mask: torch.Tensor, actions: torch.Tensor,
+                    mask_rows: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(log_prob of ``actions``, entropy) of the masked softmax over ``logits`` [B, 13527], differentiable w.r.t.
+    the logits.  ``mask`` is [B, 13527] (bool/uint8, any row stride) or, with ``mask_rows`` (int64 [B]), the whole
+    rollout mask storage indexed per row -- no minibatch gather of masks."""
+    assert logits.dim() == 2 and logits.shape[1] == nv.NUM_ACTIONS and logits.stride(1) == 1
+    assert logits.dtype in (torch.float32, torch.bfloat16)
+    assert mask.stride(-1) == 1 and mask.dtype in (torch.uint8, torch.bool) and mask.dim() == 2
+    if mask_rows is not None:
+        mask_rows = mask_rows.contiguous().long()
+    return _MaskedCategoricalEval.apply(logits, mask, actions, mask_rows)

@@ -347,3 +347,53 @@ def test_uchifuzume_fast_path_agrees_with_nested_generation():
                     if not nifu and D // 9 != (0 if side == 0 else 8) and not g.in_check(side):
                         ufz_seen += 1
     assert ufz_seen > 0
+
+
+def test_long_game_stress_mix():
+    """BASELINE config 5 in miniature: one batch mixing start positions, drop-heavy endgames and 4-ply-cycle
+    scripts that must end by sennichite on ply 13, with max-move truncation, at 262,144-env layout sizes checked
+    for memory only (state bytes) and 6,144 envs stepped against the oracle's termination histogram."""
+    import ctypes as C
+    from shogidrl_b200 import VecShogiEnv, _native as nv
+
+    offs, total = (C.c_int64 * 3)(), C.c_int64()
+    assert nv.lib().kz_state_layout(262144, 500, offs, C.byref(total)) == 0
+    assert total.value < 5 * 2**30  # 4.3 GB of state per GPU for 262,144 games with 500-ply repetition tables
+
+    dev = torch.device("cuda:0")
+    n_each, T, max_moves, seed = 2048, 90, 80, 21
+    n = 3 * n_each
+    start = orc.OracleGame().export()
+    eg = _random_endgames(n_each, 77)
+    cyc = orc.parse_sfen("4k4/9/9/9/9/R8/9/9/4K4 b - 1")
+    boards = np.concatenate([np.tile(start[0], (n_each, 1)), eg[0], np.tile(cyc[0], (n_each, 1))])
+    hands = np.concatenate([np.tile(start[1], (n_each, 1)), eg[1], np.tile(cyc[1], (n_each, 1))])
+    sides = np.concatenate([np.zeros(n_each, np.uint8), eg[2], np.zeros(n_each, np.uint8)])
+    mcs = np.zeros(n, np.int32)
+    env = VecShogiEnv(n, max_moves_per_game=max_moves, device=dev, seed=seed, auto_reset=True)
+    env.load_positions(boards, hands, sides, mcs, eval_termination=False)
+    env.step_index = 0
+    env.refresh(random_actions=True)
+    # scripted third: the 4-ply rook/king cycle; others: random legal
+    from shogidrl_b200.utils import move_to_index
+    cycle = [move_to_index(m) for m in [(5, 0, 5, 1, False), (0, 4, 0, 3, False), (5, 1, 5, 0, False), (0, 3, 0, 4, False)]]
+    reasons = []
+    senn_at = np.full(n_each, -1)
+    for t in range(T):
+        a = env.next_actions.clone()
+        if t < 13:
+            a[2 * n_each:] = cycle[t % 4]
+        out = env.step(a, random_actions=True)
+        r = out["reason"].cpu().numpy()
+        reasons.append(r.copy())
+        if t < 13:
+            assert (r[2 * n_each:] == (4 if t == 12 else 0)).all(), t  # sennichite exactly on the 13th ply
+    torch.cuda.synchronize()
+    assert int(env.errors().abs().sum()) == 0
+    reasons = np.stack(reasons)
+    # the random two thirds against the oracle (same RNG, same starts)
+    ref = orc.selfplay(2 * n_each, T, max_moves=max_moves, seed=seed, threads=os.cpu_count() or 1,
+                       start=(boards[:2 * n_each], hands[:2 * n_each], sides[:2 * n_each], mcs[:2 * n_each]))
+    assert np.array_equal(reasons[:, :2 * n_each], ref["reasons"])
+    hist = np.bincount(reasons[:, :2 * n_each].ravel(), minlength=5)
+    assert hist[1] > 0 and hist[3] > 0  # checkmates and max-move truncations both occur

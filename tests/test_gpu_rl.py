@@ -16,8 +16,8 @@ def _torch_reference(logits, mask):
     """base_actor_critic.py:64-116 in plain fp32 torch."""
     masked = torch.where(mask.bool(), logits.float(), torch.tensor(float("-inf"), device=logits.device))
     probs = torch.softmax(masked, dim=-1)
-    nan_rows = torch.isnan(probs).any(dim=1)
-    probs[nan_rows] = 1.0 / A
+    nan_rows = torch.isnan(probs).any(dim=1, keepdim=True)
+    probs = torch.where(nan_rows, torch.full_like(probs, 1.0 / A), probs)  # out of place: keeps autograd usable
     return probs, torch.distributions.Categorical(probs=probs)
 
 
@@ -129,3 +129,37 @@ def test_gae_golden_and_oracle(golden_dir):
     adv, ret = rl.gae(r.to(dev), v.to(dev), d.to(dev), lv.to(dev), 0.99, 0.95)
     a_ref, r_ref = orc.gae(r.numpy(), v.numpy(), d.numpy(), lv.numpy(), 0.99, 0.95)
     assert np.array_equal(adv.cpu().numpy(), a_ref) and np.array_equal(ret.cpu().numpy(), r_ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_evaluate_matches_torch_forward_and_backward(dtype):
+    """rl.evaluate_masked (kz_eval_masked_fwd/bwd) against the PyTorch formulation of evaluate_actions
+    (base_actor_critic.py:118-184): log-probs, entropy and the gradient w.r.t. the logits."""
+    from shogidrl_b200 import rl
+    dev = torch.device("cuda:0")
+    n = 192
+    logits, mask = _random_case(n, dev, seed=4, legal_p=0.003)
+    mask[5] = False            # a row without legal actions: uniform fallback, zero gradient
+    mask[6] = False; mask[6, 77] = True   # single legal action: p = 1 -> clamp saturates, zero log-prob gradient
+    logits = logits.to(dtype).float()
+    actions = torch.stack([torch.nonzero(mask[i])[0, 0] if mask[i].any() else torch.tensor(3, device=dev) for i in range(n)])
+    w_lp = torch.randn(n, device=dev); w_ent = torch.randn(n, device=dev)
+
+    ref_in = logits.clone().requires_grad_()
+    probs, dist = _torch_reference(ref_in, mask)
+    ref_lp, ref_ent = dist.log_prob(actions), dist.entropy()
+    ((ref_lp * w_lp).sum() + (ref_ent * w_ent).sum()).backward()
+
+    # padded storage + row indirection, as PPOAgent.learn uses it
+    store = torch.zeros(2 * n, 13536, dtype=torch.uint8, device=dev)
+    rows = torch.randperm(2 * n, device=dev)[:n]
+    store[rows, :A] = mask.to(torch.uint8)
+    x = logits.to(dtype).clone().requires_grad_()
+    lp, ent = rl.evaluate_masked(x, store[:, :A], actions, mask_rows=rows)
+    ((lp * w_lp).sum() + (ent * w_ent).sum()).backward()
+    assert torch.allclose(lp, ref_lp, rtol=1e-5, atol=2e-6), float((lp - ref_lp).abs().max())
+    assert torch.allclose(ent, ref_ent, rtol=1e-5, atol=1e-5), float((ent - ref_ent).abs().max())
+    g, g_ref = x.grad.float(), ref_in.grad
+    tol = 1e-5 if dtype == torch.float32 else 1e-2  # bf16 gradients are rounded to 8 bits of mantissa
+    assert torch.allclose(g, g_ref, rtol=tol, atol=tol * 0.1), float((g - g_ref).abs().max())
+    assert float(g[5].abs().max()) == 0.0 and bool((g[~mask.bool()] == 0).all())
