@@ -5,6 +5,8 @@ from types import SimpleNamespace
 from shogidrl_b200.core import ActorCritic, PPOAgent
 from torch.profiler import profile, ProfilerActivity
 dev = torch.device("cuda")
+import os
+torch.backends.cudnn.benchmark = os.environ.get("CUDNN_BENCH", "0") == "1"
 cfg = SimpleNamespace(env=SimpleNamespace(device="cuda", seed=1, input_channels=46, num_actions_total=13527, max_moves_per_game=500),
     training=SimpleNamespace(learning_rate=3e-4, gamma=0.99, lambda_gae=0.95, clip_epsilon=0.2, value_loss_coeff=0.5, entropy_coef=0.01,
         ppo_epochs=1, minibatch_size=16384, steps_per_epoch=65536, total_timesteps=1 << 20, gradient_clip_max_norm=0.5,
