@@ -71,7 +71,10 @@ __device__ __forceinline__ BB slide_ray(const Tables& T, int sq, int d, BB occ) 
 // Squares next to the king of `me` (on K) that an enemy piece attacks, computed on occupancy `occk`
 // (the caller removes the king itself so that sliders x-ray through its square).  64 (neighbour, direction)
 // ray probes in two warp rounds + 16 knight probes.
-__device__ __noinline__ BB king_danger(const uint32_t tab, const int K, const int me, const BB occk) {
+#ifndef KD_ATTR
+#define KD_ATTR __forceinline__  // inlined into the generator and into ufz_fast: 0.4025 -> 0.3979 ms
+#endif
+__device__ KD_ATTR BB king_danger(const uint32_t tab, const int K, const int me, const BB occk) {
   const int lane = threadIdx.x & 31;
   const WarpScratch& ws = s_ws[threadIdx.x >> 5];
   const Tables T{};
@@ -126,7 +129,10 @@ __device__ __noinline__ BB king_danger(const uint32_t tab, const int K, const in
 // (b) taking the pawn with a piece that is not pinned; blocks and drops cannot answer an adjacent check, and a
 // pinned piece can never reach D because D lies on a king ray whose first piece is the pawn itself.
 // Equivalent to "generate_all_legal_moves(enemy) is empty" (shogi_rules_logic.py:343-357).
-__device__ __noinline__ bool ufz_fast(const uint32_t tab, const int me, const int KE, const int D, const BB occ,
+#ifndef UFZ_ATTR
+#define UFZ_ATTR __forceinline__  // 0.3978 -> 0.3934 ms
+#endif
+__device__ UFZ_ATTR bool ufz_fast(const uint32_t tab, const int me, const int KE, const int D, const BB occ,
                                       const BB own) {
   const int lane = threadIdx.x & 31;
   const WarpScratch& ws = s_ws[threadIdx.x >> 5];
@@ -203,8 +209,9 @@ struct GenResult {
 template <bool EMIT>
 __device__ __noinline__ GenResult gen_moves(const uint32_t tab, const int me, const int ufz_mode);
 
-template <bool EMIT>
-__device__ __forceinline__ GenResult gen_moves_impl(const uint32_t tab, const int me, const int ufz_mode) {
+template <bool EMIT, int UFZ_STATIC = -1>  // UFZ_STATIC >= 0: the uchifuzume mode is known at compile time
+__device__ __forceinline__ GenResult gen_moves_impl(const uint32_t tab, const int me, const int ufz_mode_rt) {
+  const int ufz_mode = UFZ_STATIC >= 0 ? UFZ_STATIC : ufz_mode_rt;
   constexpr int SCR = EMIT ? 0 : 1;  // scratch set: the count-only instance runs inside the emitting one
   const int lane = threadIdx.x & 31;
   WarpScratch& ws = s_ws[threadIdx.x >> 5];
@@ -331,11 +338,13 @@ __device__ __forceinline__ GenResult gen_moves_impl(const uint32_t tab, const in
       if (lane == 0) ws.board[D] = (uint8_t)pcode;
       __syncwarp();
       bool mate;
-      if (ufz_mode == UFZ_FAST) {
+      if (UFZ_STATIC == UFZ_FAST || ufz_mode == UFZ_FAST) {
         mate = ufz_fast(tab, me, KE, D, occ, own);
-      } else {
+      } else if constexpr (UFZ_STATIC != UFZ_FAST) {
         GenResult sub = gen_moves<false>(tab, 1 - me, UFZ_SKIP);
         mate = sub.in_check && sub.count == 0;
+      } else {
+        mate = false;
       }
       __syncwarp();
       if (lane == 0) ws.board[D] = 0;
@@ -542,6 +551,9 @@ __device__ __forceinline__ uint32_t rand32(unsigned long long seed, unsigned lon
 __device__ __forceinline__ uint16_t ld_u16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
 __device__ __forceinline__ void st_u16(uint8_t* p, int v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
 
+// MODE 1 = step (the hot kernel: only the fast paths are compiled in, the generator is inlined), MODE 0 = refresh
+// (loaded positions: nested-generation uchifuzume, full key, optional termination evaluation).
+template <int MODE>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_kernel(const StepParams P) {
   for (int i = threadIdx.x; i < 81 * 8 * 3; i += blockDim.x) s_ray[i] = g_ray[i];
   for (int i = threadIdx.x; i < NCLS * 81 * 3; i += blockDim.x) s_step[i] = g_step[i];
@@ -559,7 +571,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
                      : reinterpret_cast<const uint32_t*>(P.meta + (size_t)g * 32)[lane - 24];
   };
   auto fetch_action = [&](int g) -> long long {
-    if (g >= P.n || P.mode != 1) return 0;
+    if (g >= P.n || MODE != 1) return 0;
     return P.actions_i64 ? reinterpret_cast<const long long*>(P.actions)[g]
                          : (long long)reinterpret_cast<const int*>(P.actions)[g];
   };
@@ -599,7 +611,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
     bool probe = false;  // a repetition-table probe is in flight (first window of 32 slots in probe_e)
     uint4 probe_e = make_uint4(0, 0, 0, 0);
 
-    if (P.mode == 1) {
+    if (MODE == 1) {
       if (status != 0) {
         // make_move on a finished game returns the terminal tuple again (shogi_game.py:589-593)
       } else if (a < 0 || a >= KZ_NUM_ACTIONS) {
@@ -719,10 +731,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
     // the square in front of the enemy king and the specialised test applies.  Loaded positions (refresh mode)
     // may have the side NOT to move in check: they take the nested-generation path, on every pawn-drop square
     // when that king is attacked.
-    if (P.mode == 0) key = position_key(ws, lane, side);  // loaded positions: full key
+    if (MODE == 0) key = position_key(ws, lane, side);  // loaded positions: full key
     GenResult gr;
-    if (P.mode == 1) {
-      gr = gen_moves<true>(tab, side, UFZ_FAST);
+    if constexpr (MODE == 1) {
+      gr = gen_moves_impl<true, UFZ_FAST>(tab, side, UFZ_FAST);  // inlined, fast uchifuzume path only
     } else {
       int mode = UFZ_GENERIC;
       if (ws.meta[side * 7] > 0) {
@@ -757,7 +769,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
       if (count == 0) err |= KZ_ERR_HISTORY_FULL;
       fresh_senn = count >= 4;
     }
-    if ((moved || (P.mode == 0 && P.eval_term)) && status == 0) {
+    if ((moved || (MODE == 0 && P.eval_term)) && status == 0) {
       // _check_and_update_termination_status (shogi_game.py:408-450), in the reference's order
       if (gr.count == 0) {
         if (gr.in_check) { status = KZ_TSUMI; winner = mover; }
@@ -765,7 +777,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
       } else if (move_count >= max_moves) { status = KZ_MAX_MOVES; winner = -1; }
       else if (fresh_senn) { status = KZ_SENNICHITE; winner = -1; }
     }
-    if (P.mode == 1 && status != 0) {  // _handle_real_move_return (shogi_game.py:553-572)
+    if (MODE == 1 && status != 0) {  // _handle_real_move_return (shogi_game.py:553-572)
       done_out = 1;
       reason_out = status;
       winner_out = winner;
@@ -773,7 +785,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
       if (winner >= 0) reward = winner == mover ? 1.f : -1.f;
     }
 
-    if (P.mode == 1 && status != 0 && P.auto_reset) {
+    if (MODE == 1 && status != 0 && P.auto_reset) {
       // StepManager.handle_episode_end -> game.reset() (step_manager.py:437-440; shogi_game.py:113-130)
       __syncwarp();
       if (lane < 24) reinterpret_cast<uint32_t*>(ws.board)[lane] = reinterpret_cast<const uint32_t*>(c_init_board)[lane];
@@ -1130,7 +1142,8 @@ int launch_step(void* state, int n, int hist_cap, StepParams P, cudaStream_t st)
   const int ctas_needed = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   int grid = g_sm_count * CTAS_PER_SM;
   if (grid > ctas_needed) grid = ctas_needed;
-  kz_step_kernel<<<grid, WARPS_PER_CTA * 32, 0, st>>>(P);
+  if (P.mode == 1) kz_step_kernel<1><<<grid, WARPS_PER_CTA * 32, 0, st>>>(P);
+  else kz_step_kernel<0><<<grid, WARPS_PER_CTA * 32, 0, st>>>(P);
   CK(cudaGetLastError());
   return KZ_OK;
 }
