@@ -24,14 +24,15 @@ for ln in open(dis):
     if m:
         pending.append((os.path.basename(m.group(1)), int(m.group(2)))); continue
     m = re.match(r'\s+/\*([0-9a-f]{4,})\*/\s+(.*?);', ln)
-    if m and func and 'kz_step' in func:
+    if m and func and 'kz_step_kernelILi1' in func.replace('<', 'I'):
         if pending:
             eng = [p for p in pending if p[0] == base]
             cur = eng[0][1] if eng else None
             pending = []
         seq.append(cur)
 rows = list(csv.reader(open(page)))
-h, data = rows[1], rows[2:]
+h = rows[1]
+data = [r for r in rows[2:] if len(r) >= len(h) and r[0] != h[0]]  # skip per-kernel header rows of further launches
 ci = {n: i for i, n in enumerate(h)}
 keys = ['stall_long_sb', 'stall_wait', 'stall_no_inst', 'stall_short_sb', 'stall_branch_resolving', 'stall_lg',
         'stall_mio', 'stall_math', 'stall_not_selected', 'stall_selected', 'stall_barrier', 'stall_dispatch', 'stall_drain']

@@ -6,7 +6,7 @@
 #include <string.h>
 
 #define FULL 0xffffffffu
-#define BITMAP_WORDS 424      // ceil(13527 / 32) = 423, padded to a multiple of 4
+#define BITMAP_WORDS 448      // ceil(13527 / 32) = 423, padded to 14 words per lane (k-th set bit selection)
 #ifndef WARPS_PER_CTA
 #define WARPS_PER_CTA 8
 #endif
