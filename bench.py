@@ -54,7 +54,7 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -231,7 +231,6 @@ def run_product(args):
     # memory (H2D) and the step's results + the next legal actions are read back to pinned host memory (D2H)
     h_act = torch.zeros(n, dtype=torch.int64).pin_memory()
     h_res = torch.zeros(n * 15, dtype=torch.uint8).pin_memory()
-    d_res = torch.zeros(n * 15, dtype=torch.uint8, device=dev)
     h_act.copy_(act[it[0] & 1])
     torch.cuda.synchronize(dev)
     e2e_steps = max(4, min(args.steps, 64))
@@ -239,16 +238,11 @@ def run_product(args):
     def e2e_step(i):
         a = act[i & 1]
         a.copy_(h_act, non_blocking=True)                                  # H2D 8 B/env
-        out = env.step(a, obs=obs_buf[i % SLOTS], mask=mask_buf[i % SLOTS][:, :13527], random_actions=True,
-                       next_out=env.next_actions)
-        d_res[: 4 * n].view(torch.float32).copy_(out["reward"])
-        d_res[4 * n: 5 * n].copy_(out["done"])
-        d_res[5 * n: 6 * n].copy_(out["reason"])
-        d_res[6 * n: 7 * n].view(torch.int8).copy_(out["winner"])
-        d_res[7 * n:].view(torch.int64).copy_(env.next_actions)
-        h_res.copy_(d_res, non_blocking=True)                              # D2H 15 B/env
+        env.step(a, obs=obs_buf[i % SLOTS], mask=mask_buf[i % SLOTS][:, :13527], random_actions=True,
+                 next_out=env.next_actions)
+        h_res.copy_(env.results, non_blocking=True)                        # D2H 15 B/env: next action, reward, done, reason, winner
         torch.cuda.current_stream(dev).synchronize()
-        h_act.copy_(h_res[7 * n:].view(torch.int64))                       # host-side hand-over of the chosen actions
+        h_act.copy_(h_res[: 8 * n].view(torch.int64))                      # host-side hand-over of the chosen actions
 
     for i in range(3):
         e2e_step(i)

@@ -112,4 +112,44 @@ class ParallelManager:
                 "sync_stats": self.model_sync.get_sync_stats()}
 
 
-__all__ = ["ParallelManager", "ModelSynchronizer", "compress_array", "decompress_array"]
+class WorkerCommunicator:
+    """Name-compatible stand-in for the mp.Queue plumbing of keisei/training/parallel/communication.py:22-236.
+    There are no worker processes to talk to: control commands and model pushes are accepted and counted, and
+    ``collect_experiences`` has nothing queued because rollouts are produced in-process by ParallelManager."""
+
+    def __init__(self, num_workers: int, max_queue_size: int = 1000, timeout: float = 10.0):
+        self.num_workers, self.max_queue_size, self.timeout = num_workers, max_queue_size, timeout
+        self.commands_sent = 0
+        self.model_updates_sent = 0
+
+    def send_control_command(self, command: str, data: Optional[Dict] = None, worker_ids=None) -> None:
+        self.commands_sent += 1
+
+    def send_model_weights(self, model_state_dict: Dict[str, torch.Tensor], worker_ids=None,
+                           compression_enabled: bool = True) -> None:
+        self.model_updates_sent += 1  # same process, same weights: nothing to ship
+
+    def collect_experiences(self):
+        return []
+
+    def get_queue_info(self) -> Dict[str, Any]:
+        return {"num_workers": self.num_workers, "queued_batches": 0}
+
+    def cleanup(self) -> None:
+        pass
+
+
+class SelfPlayWorker:
+    """Name-compatible stand-in for keisei/training/parallel/self_play_worker.py:27-463.  A "worker" here is a
+    contiguous slice of envs of one VecShogiEnv batch, not an OS process; ``run`` is therefore not available."""
+
+    def __init__(self, worker_id: int, env_slice: slice):
+        self.worker_id, self.env_slice = worker_id, env_slice
+
+    def run(self) -> None:  # pragma: no cover - documented non-feature
+        raise RuntimeError("self-play runs on the device inside ParallelManager.collect_experiences; "
+                           "there are no worker processes to start")
+
+
+__all__ = ["ParallelManager", "ModelSynchronizer", "WorkerCommunicator", "SelfPlayWorker", "compress_array",
+           "decompress_array"]

@@ -36,13 +36,17 @@ class VecShogiEnv:
         self.obs = torch.zeros((self.n, 46, 9, 9), dtype=torch.float32, device=d)
         self._mask_store = torch.zeros((self.n, nv.MASK_PAD_STRIDE), dtype=torch.uint8, device=d)
         self.mask = self._mask_store[:, : nv.NUM_ACTIONS]  # uint8 view, row stride 13536
-        self.reward = torch.zeros(self.n, dtype=torch.float32, device=d)
-        self.done = torch.zeros(self.n, dtype=torch.uint8, device=d)
-        self.reason = torch.zeros(self.n, dtype=torch.uint8, device=d)
-        self.winner = torch.zeros(self.n, dtype=torch.int8, device=d)
+        # per-step scalar results live in ONE contiguous buffer (15 bytes per env: next_actions i64, reward f32,
+        # done u8, reason u8, winner i8) so that a host consumer fetches them with a single device-to-host copy
+        n = self.n
+        self.results = torch.zeros(15 * n, dtype=torch.uint8, device=d)
+        self.next_actions = self.results[: 8 * n].view(torch.int64)
+        self.reward = self.results[8 * n: 12 * n].view(torch.float32)
+        self.done = self.results[12 * n: 13 * n]
+        self.reason = self.results[13 * n: 14 * n]
+        self.winner = self.results[14 * n:].view(torch.int8)
         self.ep_len = torch.zeros(self.n, dtype=torch.int32, device=d)
         self.legal_count = torch.zeros(self.n, dtype=torch.int32, device=d)
-        self.next_actions = torch.zeros(self.n, dtype=torch.int64, device=d)
         self.step_index = 0
         self.reset()
 

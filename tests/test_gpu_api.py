@@ -206,3 +206,17 @@ def test_parallel_manager_shim():
     assert bool(buf.legal_masks[:64].gather(1, buf.actions[:64, None]).all())
     pm.stop_workers()
     assert not pm.is_healthy() and pm.get_parallel_stats()["total_steps_collected"] == 64
+
+
+def test_batched_evaluation_games():
+    from shogidrl_b200.core import ActorCritic, PPOAgent
+    from shogidrl_b200.evaluation import evaluate_vs_opponent
+    cfg = make_config()
+    torch.manual_seed(3)
+    agent = PPOAgent(ActorCritic(46, 13527), cfg, torch.device("cuda"), use_mixed_precision=True)
+    res = evaluate_vs_opponent(agent, 64, num_envs=64, max_moves_per_game=60, seed=9, deterministic=False)
+    assert res.games >= 64 and res.agent_wins + res.opponent_wins + res.draws == res.games
+    assert 0 < res.mean_length <= 60 and 0.0 <= res.win_rate <= 1.0
+    # agent vs agent also runs
+    res2 = evaluate_vs_opponent(agent, 16, opponent=agent, num_envs=16, max_moves_per_game=30, deterministic=False)
+    assert res2.games >= 16
