@@ -13,9 +13,6 @@
 #ifndef MIN_CTAS_PER_SM
 #define MIN_CTAS_PER_SM 3  // 80 registers per thread: 24 warps per SM (measured best: 2 -> 0.423 ms, 3 -> 0.402 ms, 4 spills)
 #endif
-#ifndef SYNC_MODE
-#define SYNC_MODE 0
-#endif
 #ifndef CTAS_PER_SM
 #define CTAS_PER_SM 3  // persistent grid = SMs x resident CTAs
 #endif

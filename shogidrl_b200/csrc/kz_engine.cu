@@ -24,7 +24,6 @@ namespace {
 __device__ uint32_t g_ray[81 * 8 * 3];
 __device__ uint32_t g_step[NCLS * 81 * 3];
 __device__ uint32_t g_init_bitmap[BITMAP_WORDS];  // legal bitmap of the start position (30 moves)
-__device__ int g_tables_ready = 0;
 
 __constant__ uint8_t c_init_board[96];  // start position; bytes 84..95 = words x, y, z of its position key
 __constant__ uint32_t c_init_key_w;     // word w of that key

@@ -31,9 +31,115 @@ __device__ __forceinline__ uint32_t hash_u32(unsigned long long seed, unsigned l
   return (uint32_t)(x >> 32);
 }
 
-// One warp per row.  Element order for the inverse CDF: lane-major (lane 0's elements 0,32,64,..., then
-// lane 1's, ...), a fixed permutation of the action axis, so the sampled law is the masked softmax.
-__global__ void __launch_bounds__(256) kz_sample_kernel(const void* logits, int bf16, long long ld, const uint8_t* mask,
+// The legal mask of a row is ~0.5 % dense, so every kernel below scans it 16 bytes per lane per load and touches
+// logits only at legal entries.  A row is cut into 16-byte windows aligned in memory (whatever the row's own
+// alignment); the partial windows at both ends are assembled from byte loads, so no access leaves the row.
+struct MaskWindows {
+  const uint8_t* row;
+  int shift;  // row address minus the aligned address of window 0
+  int nw;
+  __device__ __forceinline__ explicit MaskWindows(const uint8_t* r) : row(r) {
+    shift = (int)(reinterpret_cast<uintptr_t>(r) & 15);
+    nw = (KZ_NUM_ACTIONS + shift + 15) >> 4;
+  }
+  __device__ __forceinline__ int first(int w) const { return (w << 4) - shift; }  // action index of byte 0 of window w
+  // the 16 mask bytes of window w (non-zero = legal); bytes outside the row read as 0
+  __device__ __forceinline__ uint4 load(int w) const {
+    const int lo = first(w);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (w >= nw) return v;
+    if (lo >= 0 && lo + 16 <= KZ_NUM_ACTIONS) {
+      v = __ldg(reinterpret_cast<const uint4*>(row + lo));
+    } else {
+      uint32_t q[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int b = 0; b < 16; b++) {
+        const int i = lo + b;
+        if (i >= 0 && i < KZ_NUM_ACTIONS && row[i]) q[b >> 2] |= 1u << ((b & 3) * 8);
+      }
+      v = make_uint4(q[0], q[1], q[2], q[3]);
+    }
+    return v;
+  }
+};
+
+// Compacted list of a row's legal actions in the warp's shared-memory slice.  Scanning the mask lane by lane and
+// touching the logits inside that scan would serialise one dependent gather per legal action (a handful of
+// lanes active each time); compacting first lets all lanes gather at once.  LIST_CAP covers any Shogi position
+// (<= 593 legal moves) in one piece; denser masks are processed in several pieces.
+#define MASK_MLP 4                      // window loads in flight per lane
+#define LIST_CAP (32 * MASK_MLP * 16)   // one group of windows always fits
+struct LegalList {
+  uint16_t* buf;
+  int cnt;
+  bool whole;  // buf holds every legal action of the row: later passes replay it instead of rescanning
+};
+
+// f(action index) for every legal action of the row, a fixed order, all lanes taking list entries round-robin
+// (entry j of a piece goes to lane j % 32)
+template <class F>
+__device__ __forceinline__ void each_legal_of_row(const MaskWindows& W, int lane, LegalList& ll, F&& f) {
+  if (!ll.whole) {
+    ll.cnt = 0;
+    bool flushed = false;
+    uint4 nx[MASK_MLP];  // next group's windows, loaded one group ahead of their compaction
+#pragma unroll
+    for (int k = 0; k < MASK_MLP; k++) nx[k] = W.load(lane + 32 * k);
+    for (int w0 = lane; w0 - lane < W.nw; w0 += 32 * MASK_MLP) {
+      uint4 v[MASK_MLP];
+#pragma unroll
+      for (int k = 0; k < MASK_MLP; k++) {
+        v[k] = nx[k];
+        nx[k] = W.load(w0 + 32 * (MASK_MLP + k));
+      }
+      int c = 0;
+#pragma unroll
+      for (int k = 0; k < MASK_MLP; k++) {
+        if (!(v[k].x | v[k].y | v[k].z | v[k].w)) continue;
+        v[k].x = __vcmpne4(v[k].x, 0); v[k].y = __vcmpne4(v[k].y, 0);
+        v[k].z = __vcmpne4(v[k].z, 0); v[k].w = __vcmpne4(v[k].w, 0);
+        c += (__popc(v[k].x) + __popc(v[k].y) + __popc(v[k].z) + __popc(v[k].w)) >> 3;
+      }
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+      const int total = __shfl_sync(FULL, incl, 31);
+      if (ll.cnt + total > LIST_CAP) {  // piece full: consume it
+        __syncwarp();
+        for (int j = lane; j < ll.cnt; j += 32) f((int)ll.buf[j]);
+        __syncwarp();
+        ll.cnt = 0;
+        flushed = true;
+      }
+      int at = ll.cnt + incl - c;
+#pragma unroll
+      for (int k = 0; k < MASK_MLP; k++) {
+        if (!(v[k].x | v[k].y | v[k].z | v[k].w)) continue;
+        const uint32_t q[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+        const int lo = W.first(w0 + 32 * k);
+#pragma unroll
+        for (int h = 0; h < 4; h++) {
+          uint32_t z = q[h];
+          while (z) {
+            const int b = (__ffs(z) - 1) >> 3;
+            z &= ~(0xFFu << (b * 8));
+            ll.buf[at++] = (uint16_t)(lo + h * 4 + b);
+          }
+        }
+      }
+      ll.cnt += total;
+    }
+    ll.whole = !flushed;
+    __syncwarp();
+  }
+  for (int j = lane; j < ll.cnt; j += 32) f((int)ll.buf[j]);
+  if (!ll.whole) __syncwarp();  // the next scan overwrites the slice
+}
+
+// One warp per row.  Element order for the inverse CDF: lane-major over the mask windows (lane 0's windows
+// 0, 32, 64, ... in ascending action order, then lane 1's, ...), a fixed permutation of the action axis, so the
+// sampled law is the masked softmax.
+__global__ void __launch_bounds__(256, 4) kz_sample_kernel(const void* logits, int bf16, long long ld, const uint8_t* mask,
                                                         long long ldm, int n, unsigned long long seed,
                                                         unsigned long long offset, void* actions, int actions_i64,
                                                         float* logp, float* entropy, int deterministic) {
@@ -41,26 +147,25 @@ __global__ void __launch_bounds__(256) kz_sample_kernel(const void* logits, int 
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
   const char* lrow = reinterpret_cast<const char*>(logits) + (size_t)row * ld * (bf16 ? 2 : 4);
-  const uint8_t* mrow = mask + (size_t)row * ldm;
+  const MaskWindows W(mask + (size_t)row * ldm);
+  __shared__ uint16_t s_list[8][LIST_CAP];
+  LegalList ll{s_list[threadIdx.x >> 5], 0, false};
   const int A = KZ_NUM_ACTIONS;
 
-  // pass 1: online max / sum of exp over legal entries; track the per-lane argmax (lowest index on ties)
+  // pass 1: online max / sum of exp over this lane's share of the legal entries; per-lane argmax (lowest index on ties)
   float m = -INFINITY, s = 0.f;
-  int amax = -1;
-  for (int i = lane; i < A; i += 32) {
-    if (mrow[i]) {
-      const float x = ld_logit(lrow, i, bf16);
-      if (x > m) { s = s * expf(m - x) + 1.f; m = x; amax = i; }
-      else s += expf(x - m);
-    }
-  }
+  int amax = 0x7fffffff;
+  each_legal_of_row(W, lane, ll, [&](int i) {
+    const float x = ld_logit(lrow, i, bf16);
+    if (x > m) { s = s * expf(m - x) + 1.f; m = x; amax = i; }
+    else { s += expf(x - m); if (x == m && i < amax) amax = i; }
+  });
   float M = m;
 #pragma unroll
   for (int o = 16; o; o >>= 1) M = fmaxf(M, __shfl_xor_sync(FULL, M, o));
-  const bool any_legal = M > -INFINITY || __any_sync(FULL, amax >= 0);
   long long act = -1;
   float lp = 0.f, ent = 0.f;
-  if (!any_legal || !(M > -INFINITY)) {
+  if (!(M > -INFINITY)) {
     // no legal entry (or all legal logits are -inf): softmax is NaN -> uniform over all actions
     // (base_actor_critic.py:93-101)
     const float p = 1.0f / (float)A;
@@ -74,17 +179,16 @@ __global__ void __launch_bounds__(256) kz_sample_kernel(const void* logits, int 
 #pragma unroll
     for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
     const float inv = 1.0f / tot;
-    int pick = -1;
-    if (deterministic) {
-      // argmax of probs == argmax of legal logits; lowest index wins ties
-      int cand = (m == M) ? amax : 0x7fffffff;
+    // argmax of probs == argmax of legal logits; lowest index wins ties
+    int best = (m == M) ? amax : 0x7fffffff;
 #pragma unroll
-      for (int o = 16; o; o >>= 1) cand = min(cand, __shfl_xor_sync(FULL, cand, o));
-      pick = cand;
-    } else {
+    for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(FULL, best, o));
+    int pick = best;
+    if (!deterministic) {
+      // inverse CDF in the order "lane 0's entries, lane 1's entries, ...": find the lane L holding the target,
+      // then lane L walks its own entries (1/32 of the legal actions)
       const float u = (float)(hash_u32(seed, offset + row) >> 8) * (1.0f / 16777216.0f);
       const float target = u * tot;
-      // lane prefix
       float incl = mys;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
@@ -94,24 +198,20 @@ __global__ void __launch_bounds__(256) kz_sample_kernel(const void* logits, int 
         const uint32_t have = __ballot_sync(FULL, mys > 0.f);
         L = 31 - __clz(have);
       }
-      const float base = __shfl_sync(FULL, incl - mys, L);
-      // walk lane L's elements (L, L+32, ...) 32 at a time
-      float run = base;
-      int lastlegal = -1;
-      for (int j0 = 0; j0 * 32 + L < A && pick < 0; j0 += 32) {
-        const int i = (j0 + lane) * 32 + L;
-        float e = 0.f;
-        if (i < A && mrow[i]) e = expf(ld_logit(lrow, i, bf16) - M);
-        float sc = e;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(FULL, sc, o); if (lane >= o) sc += t; }
-        const uint32_t h = __ballot_sync(FULL, e > 0.f && run + sc > target);
-        const uint32_t lg = __ballot_sync(FULL, e > 0.f);
-        if (h) pick = (j0 + __ffs(h) - 1) * 32 + L;
-        if (lg) lastlegal = (j0 + 31 - __clz(lg)) * 32 + L;
-        run += __shfl_sync(FULL, sc, 31);
-      }
-      if (pick < 0) pick = lastlegal;
+      float run = incl - mys;
+      int found = -1, last = -1;
+      each_legal_of_row(W, lane, ll, [&](int i) {
+        if (lane != L) return;
+        const float e = expf(ld_logit(lrow, i, bf16) - M);
+        if (e > 0.f) {
+          last = i;
+          run += e;
+          if (found < 0 && run > target) found = i;
+        }
+      });
+      if (found < 0) found = last;
+      found = __shfl_sync(FULL, found, L);
+      if (found >= 0) pick = found;  // (< 0: every exp underflowed on the re-read; keep the argmax)
     }
     act = pick;
     // Categorical(probs=p): logits = log(clamp(p, eps, 1 - eps)) with eps = FLT_EPSILON
@@ -122,11 +222,10 @@ __global__ void __launch_bounds__(256) kz_sample_kernel(const void* logits, int 
     }
     if (entropy) {
       float h = 0.f;
-      for (int i = lane; i < A; i += 32)
-        if (mrow[i]) {
-          const float p = expf(ld_logit(lrow, i, bf16) - M) * inv;
-          h -= p * logf(fminf(fmaxf(p, eps), 1.0f - eps));
-        }
+      each_legal_of_row(W, lane, ll, [&](int i) {
+        const float p = expf(ld_logit(lrow, i, bf16) - M) * inv;
+        h -= p * logf(fminf(fmaxf(p, eps), 1.0f - eps));
+      });
 #pragma unroll
       for (int o = 16; o; o >>= 1) h += __shfl_xor_sync(FULL, h, o);
       ent = h;
@@ -215,7 +314,7 @@ __device__ __forceinline__ float ent_g(float p, float eps) {  // dH/dp for H = -
   return -(logf(p) + 1.0f);
 }
 
-__global__ void __launch_bounds__(256) kz_eval_fwd_kernel(const void* logits, int bf16, long long ld, const uint8_t* mask,
+__global__ void __launch_bounds__(256, 4) kz_eval_fwd_kernel(const void* logits, int bf16, long long ld, const uint8_t* mask,
                                                           long long ldm, const long long* mask_rows, const long long* actions,
                                                           int n, float* logp, float* entropy, float* saved /*[n][4]*/) {
   const int lane = threadIdx.x & 31;
@@ -223,15 +322,17 @@ __global__ void __launch_bounds__(256) kz_eval_fwd_kernel(const void* logits, in
   if (row >= n) return;
   const char* lrow = reinterpret_cast<const char*>(logits) + (size_t)row * ld * (bf16 ? 2 : 4);
   const uint8_t* mrow = mask + (size_t)(mask_rows ? mask_rows[row] : row) * ldm;
+  const MaskWindows W(mrow);
+  __shared__ uint16_t s_list[8][LIST_CAP];
+  LegalList ll{s_list[threadIdx.x >> 5], 0, false};
   const int A = KZ_NUM_ACTIONS;
   const float eps = FLT_EPSILON;
   float m = -INFINITY, s = 0.f;
-  for (int i = lane; i < A; i += 32)
-    if (mrow[i]) {
-      const float x = ld_logit(lrow, i, bf16);
-      if (x > m) { s = s * expf(m - x) + 1.f; m = x; }
-      else s += expf(x - m);
-    }
+  each_legal_of_row(W, lane, ll, [&](int i) {
+    const float x = ld_logit(lrow, i, bf16);
+    if (x > m) { s = s * expf(m - x) + 1.f; m = x; }
+    else s += expf(x - m);
+  });
   float M = m;
 #pragma unroll
   for (int o = 16; o; o >>= 1) M = fmaxf(M, __shfl_xor_sync(FULL, M, o));
@@ -247,12 +348,11 @@ __global__ void __launch_bounds__(256) kz_eval_fwd_kernel(const void* logits, in
     Z = z;
     const float inv = 1.0f / Z;
     float h = 0.f, sg = 0.f;
-    for (int i = lane; i < A; i += 32)
-      if (mrow[i]) {
-        const float p = expf(ld_logit(lrow, i, bf16) - M) * inv;
-        h -= p * logf(fminf(fmaxf(p, eps), 1.0f - eps));
-        sg += ent_g(p, eps) * p;
-      }
+    each_legal_of_row(W, lane, ll, [&](int i) {
+      const float p = expf(ld_logit(lrow, i, bf16) - M) * inv;
+      h -= p * logf(fminf(fmaxf(p, eps), 1.0f - eps));
+      sg += ent_g(p, eps) * p;
+    });
 #pragma unroll
     for (int o = 16; o; o >>= 1) { h += __shfl_xor_sync(FULL, h, o); sg += __shfl_xor_sync(FULL, sg, o); }
     ent = h; S = sg;
@@ -267,7 +367,18 @@ __global__ void __launch_bounds__(256) kz_eval_fwd_kernel(const void* logits, in
   }
 }
 
-__global__ void __launch_bounds__(256) kz_eval_bwd_kernel(const void* logits, int bf16, long long ld, const uint8_t* mask,
+// zero `bytes` bytes at p (2-byte aligned, even length) with one warp: 16-byte stores between 2-byte edges
+__device__ __forceinline__ void zero_row(char* p, size_t bytes, int lane) {
+  const size_t head = min((size_t)((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15), bytes);
+  const size_t body = (bytes - head) & ~(size_t)15;
+  if ((size_t)lane * 2 < head) *reinterpret_cast<uint16_t*>(p + lane * 2) = 0;
+  uint4* q = reinterpret_cast<uint4*>(p + head);
+  for (size_t k = lane; k < body / 16; k += 32) q[k] = make_uint4(0, 0, 0, 0);
+  const size_t tail = bytes - head - body;
+  if ((size_t)lane * 2 < tail) *reinterpret_cast<uint16_t*>(p + head + body + lane * 2) = 0;
+}
+
+__global__ void __launch_bounds__(256, 4) kz_eval_bwd_kernel(const void* logits, int bf16, long long ld, const uint8_t* mask,
                                                           long long ldm, const long long* mask_rows, const long long* actions,
                                                           int n, const float* dlogp, const float* dent, const float* saved,
                                                           void* dlogits, long long ldg) {
@@ -287,15 +398,20 @@ __global__ void __launch_bounds__(256) kz_eval_bwd_kernel(const void* logits, in
   float pa = 0.f;
   if (!dead && a >= 0 && a < A && mrow[a]) pa = expf(ld_logit(lrow, (int)a, bf16) - M) * inv;
   const float wl = (pa > eps && pa < 1.0f - eps) ? gl : 0.f;  // clamp passes gradient only inside (eps, 1 - eps)
-  for (int i = lane; i < A; i += 32) {
-    float g = 0.f;
-    if (!dead && mrow[i]) {
-      const float p = expf(ld_logit(lrow, i, bf16) - M) * inv;
-      g = ge * p * (ent_g(p, eps) - S) + wl * ((i == a ? 1.f : 0.f) - p);
-    }
+  // dlogits is zero except at legal actions: clear the row with 16-byte stores, then scatter the legal entries
+  const int esz = bf16 ? 2 : 4;
+  zero_row(grow, (size_t)A * esz, lane);
+  if (dead) return;
+  __syncwarp();  // orders the clearing stores before the scattered ones (different lanes, same addresses)
+  const MaskWindows W(mrow);
+  __shared__ uint16_t s_list[8][LIST_CAP];
+  LegalList ll{s_list[threadIdx.x >> 5], 0, false};
+  each_legal_of_row(W, lane, ll, [&](int i) {
+    const float p = expf(ld_logit(lrow, i, bf16) - M) * inv;
+    const float g = ge * p * (ent_g(p, eps) - S) + wl * ((i == a ? 1.f : 0.f) - p);
     if (bf16) reinterpret_cast<__nv_bfloat16*>(grow)[i] = __float2bfloat16(g);
     else reinterpret_cast<float*>(grow)[i] = g;
-  }
+  });
 }
 
 }  // namespace

@@ -75,7 +75,8 @@ class _MaskedCategoricalEval(torch.autograd.Function):
         dev = logits.device
         n = logits.shape[0]
         ldg = (nv.NUM_ACTIONS + 15) // 16 * 16
-        store = torch.zeros((n, ldg), dtype=logits.dtype, device=dev)  # padded rows: vector-friendly for the GEMM backward
+        store = torch.empty((n, ldg), dtype=logits.dtype, device=dev)  # 16-byte aligned rows; the kernel clears [0, A)
+        store[:, nv.NUM_ACTIONS:].zero_()
         nv.check(nv.lib().kz_eval_masked_bwd(logits.data_ptr(), int(logits.dtype == torch.bfloat16), logits.stride(0),
                                              mask.data_ptr(), mask.stride(0), nv.ptr(ctx.mask_rows), actions.data_ptr(), n,
                                              dlogp.contiguous().float().data_ptr(), dent.contiguous().float().data_ptr(),

@@ -163,3 +163,52 @@ def test_fused_evaluate_matches_torch_forward_and_backward(dtype):
     tol = 1e-5 if dtype == torch.float32 else 1e-2  # bf16 gradients are rounded to 8 bits of mantissa
     assert torch.allclose(g, g_ref, rtol=tol, atol=tol * 0.1), float((g - g_ref).abs().max())
     assert float(g[5].abs().max()) == 0.0 and bool((g[~mask.bool()] == 0).all())
+
+
+@pytest.mark.parametrize("legal_p", [0.25, 1.0])
+def test_dense_masks_take_the_multi_piece_path(legal_p):
+    """Masks far denser than any Shogi position overflow the per-row compaction list and are consumed in
+    pieces; unaligned rows (row stride 13527) exercise the byte-assembled edge windows.  Same law, same numbers."""
+    from shogidrl_b200 import rl
+    dev = torch.device("cuda:0")
+    n = 96
+    logits, mask = _random_case(n, dev, seed=9, legal_p=legal_p)
+    assert mask.stride(0) == A  # rows start at every alignment mod 16
+    act, logp, ent = rl.sample_masked(logits, mask, seed=5, offset=0, want_entropy=True)
+    assert bool(mask.gather(1, act[:, None]).all())
+    probs, dist = _torch_reference(logits, mask)
+    assert torch.allclose(logp, dist.log_prob(act), rtol=1e-5, atol=2e-6)
+    assert torch.allclose(ent, dist.entropy(), rtol=1e-5, atol=1e-5)
+    det, _, _ = rl.sample_masked(logits, mask, deterministic=True)
+    assert torch.equal(det, torch.argmax(probs, dim=-1))
+    # fused evaluation, forward and backward
+    w_lp = torch.randn(n, device=dev); w_ent = torch.randn(n, device=dev)
+    ref_in = logits.clone().requires_grad_()
+    _, rdist = _torch_reference(ref_in, mask)
+    ((rdist.log_prob(act) * w_lp).sum() + (rdist.entropy() * w_ent).sum()).backward()
+    x = logits.clone().requires_grad_()
+    lp, e2 = rl.evaluate_masked(x, mask, act)
+    ((lp * w_lp).sum() + (e2 * w_ent).sum()).backward()
+    assert torch.allclose(lp, rdist.log_prob(act).detach(), rtol=1e-5, atol=2e-6)
+    assert torch.allclose(e2, rdist.entropy().detach(), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(x.grad, ref_in.grad, rtol=1e-4, atol=1e-6), float((x.grad - ref_in.grad).abs().max())
+
+
+def test_dense_mask_sampling_law():
+    """Inverse-CDF over a 2,000-entry support (several list pieces per lane): empirical frequencies of the 20
+    heaviest actions match the softmax within 5 sigma."""
+    from shogidrl_b200 import rl
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(21)
+    row_logits = (torch.randn(A, generator=g) * 2).to(dev)
+    row_mask = torch.zeros(A, dtype=torch.bool, device=dev)
+    row_mask[torch.randperm(A, generator=g)[:6000].to(dev)] = True
+    n = 65536
+    logits = row_logits.expand(n, A).contiguous()
+    mask = row_mask.expand(n, A).contiguous()
+    act, _, _ = rl.sample_masked(logits, mask, seed=123, offset=0)
+    probs, _ = _torch_reference(logits[:1], mask[:1])
+    top = torch.topk(probs[0], 20).indices
+    freq = torch.bincount(act, minlength=A).float() / n
+    sigma = torch.sqrt(probs[0, top] * (1 - probs[0, top]) / n)
+    assert bool(((freq[top] - probs[0, top]).abs() < 5 * sigma + 1e-6).all())
