@@ -205,3 +205,27 @@ def pack_sfen(sfen_str: str):
     if int(num) < 1:
         raise ValueError("SFEN move number must be positive")
     return b, h, 0 if turn == "b" else 1, int(num) - 1
+
+
+class HostPosition:
+    """Host snapshot of one device game with the facade's attribute names (``board``, ``hands``, ``current_player``,
+    ``move_count``, ``game_over``, ``winner``, ``termination_reason``, ``move_history``), enough for the text
+    writers here and in kif.py.  Built by ``VecShogiEnv.to_games`` from kz_export_positions output."""
+
+    _REASONS = {0: None, 1: "Tsumi", 2: "stalemate", 3: "Max moves reached", 4: "Sennichite"}
+
+    def __init__(self, board_codes, hands14, side: int, move_count: int, status: int = 0, winner: int = -1):
+        self.board = [[Piece.from_code(int(board_codes[r * 9 + c])) for c in range(9)] for r in range(9)]
+        self.hands = {color: {PieceType(t): int(hands14[color * 7 + t]) for t in range(7)} for color in (0, 1)}
+        self.current_player = Color(int(side))
+        self.move_count = int(move_count)
+        self.game_over = int(status) != 0
+        self.termination_reason = self._REASONS.get(int(status))
+        self.winner = Color(int(winner)) if int(winner) in (0, 1) else None
+        self.move_history = []
+
+    def to_sfen_string(self) -> str:
+        return game_to_sfen(self)
+
+    def to_string(self) -> str:
+        return game_to_text(self)

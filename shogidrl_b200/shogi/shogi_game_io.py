@@ -1,0 +1,13 @@
+"""Names of keisei/shogi/shogi_game_io.py for callers that import the I/O helpers directly."""
+from .kif import game_to_kif  # noqa: F401
+from .sfen import board_from_sfen_segment as populate_board_from_sfen_segment  # noqa: F401
+from .sfen import encode_move as encode_move_to_sfen_string  # noqa: F401
+from .sfen import game_to_sfen as convert_game_to_sfen_string  # noqa: F401
+from .sfen import game_to_text as convert_game_to_text_representation  # noqa: F401
+from .sfen import hands_from_sfen_segment as populate_hands_from_sfen_segment  # noqa: F401
+from .sfen import sfen_to_move_tuple, split_sfen as parse_sfen_string_components  # noqa: F401
+
+
+def generate_neural_network_observation(game):
+    """46 x 9 x 9 observation of ``game`` (shogi_game_io.py:434-539), computed by the device engine."""
+    return game.get_observation()

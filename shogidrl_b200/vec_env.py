@@ -152,6 +152,27 @@ class VecShogiEnv:
                                              m.data_ptr(), self._sp()), "kz_export_positions")
         return b, h, m
 
+    def to_games(self, env_ids=None):
+        """Host snapshots (``shogi.sfen.HostPosition``) of the selected device games: SFEN / board text / KIF
+        headers for debugging, parity dumps and displays.  One export launch + one D2H."""
+        from .shogi.sfen import HostPosition
+        b, h, m = [x.cpu().numpy() for x in self.export()]
+        ids = range(self.n) if env_ids is None else [int(i) for i in env_ids]
+        return [HostPosition(b[i], h[i], m[i, 0], m[i, 1], status=m[i, 3], winner=m[i, 4]) for i in ids]
+
+    def to_sfen(self, env_ids=None):
+        """SFEN strings of the selected device games (shogi_game_io.py:312-379 format)."""
+        return [g.to_sfen_string() for g in self.to_games(env_ids)]
+
+    def load_sfens(self, sfens, eval_termination: bool = True):
+        """ShogiGame.from_sfen (shogi_game.py:283-345) for a whole batch: one SFEN per env."""
+        from .shogi.sfen import pack_sfen
+        assert len(sfens) == self.n
+        packed = [pack_sfen(s) for s in sfens]
+        return self.load_positions(np.stack([p[0] for p in packed]), np.stack([p[1] for p in packed]),
+                                   np.asarray([p[2] for p in packed], np.uint8), np.asarray([p[3] for p in packed], np.int32),
+                                   eval_termination=eval_termination)
+
     def errors(self, clear: bool = False) -> torch.Tensor:
         out = torch.empty(self.n, dtype=torch.int32, device=self.device)
         nv.check(self._L.kz_errors(self.state.data_ptr(), self.n, self.hist_cap, out.data_ptr(), int(clear), self._sp()),

@@ -220,3 +220,42 @@ def test_batched_evaluation_games():
     # agent vs agent also runs
     res2 = evaluate_vs_opponent(agent, 16, opponent=agent, num_envs=16, max_moves_per_game=30, deterministic=False)
     assert res2.games >= 16
+
+
+def test_device_batch_sfen_dump_load_and_kif(golden_dir):
+    """f-3: device games -> SFEN / text / KIF and back.  A batch replays golden traces on the device; its dumps
+    equal the reference's strings ply by ply, and reloading the dumped SFENs reproduces the legal masks."""
+    import json
+    from shogidrl_b200.shogi import ShogiGame
+    from shogidrl_b200.shogi.kif import game_to_kif
+    from shogidrl_b200.utils import PolicyOutputMapper
+    from shogidrl_b200.vec_env import VecShogiEnv
+    with open(os.path.join(golden_dir, "io_golden.json"), encoding="utf-8") as f:
+        games = json.load(f)["games"]
+    dev = torch.device("cuda:0")
+    n = len(games)
+    T = min(len(g["plies"]) for g in games) - 1   # stop before any game ends: no auto-reset in the comparison
+    env = VecShogiEnv(n, max_moves_per_game=500, device=dev)
+    env.reset()
+    for t in range(T):
+        env.step(torch.tensor([g["plies"][t]["action"] for g in games], device=dev))
+        if t % 9 == 0 or t == T - 1:
+            assert env.to_sfen() == [g["plies"][t]["sfen"] for g in games]
+            assert [p.to_string() for p in env.to_games()] == [g["plies"][t]["text"] for g in games]
+    mask_before = env.mask.clone()
+    env2 = VecShogiEnv(n, max_moves_per_game=500, device=dev)
+    env2.load_sfens(env.to_sfen())
+    assert torch.equal(env2.mask, mask_before)
+    assert int(env.errors().abs().sum()) == 0
+    # scalar facade: the KIF of a replayed game equals the reference's export
+    mapper = PolicyOutputMapper()
+    g0 = games[0]
+    game = ShogiGame(max_moves_per_game=g0["max_moves"], device=dev)
+    for t, ply in enumerate(g0["plies"]):
+        game.make_move(mapper.policy_index_to_shogi_move(ply["action"]))
+        if str(t) in g0["kif"]:
+            kif = game_to_kif(game, sente_player_name="A", gote_player_name="B")
+            kif = "\n".join("*Date: X" if ln.startswith("*Date:") else ln for ln in kif.split("\n"))
+            assert kif == g0["kif"][str(t)]
+        if t >= 45:
+            break
