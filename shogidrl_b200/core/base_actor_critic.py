@@ -2,8 +2,9 @@
 
 ``get_action_and_value`` keeps the signature of keisei/core/base_actor_critic.py:43-116 but, after the PyTorch
 forward pass (the only dense contraction on the path), the masked softmax / Categorical sample / log-prob run in
-one hand-written kernel (kz_sample_masked).  ``evaluate_actions`` (:118-184) needs gradients and stays in PyTorch
-with the same formulas (Categorical(probs) clamps probabilities to [eps, 1 - eps] before the log).
+one hand-written kernel (kz_sample_masked).  ``evaluate_actions`` (:118-184) runs the same formulas
+(Categorical(probs) clamps probabilities to [eps, 1 - eps] before the log) as a fused forward/backward kernel pair
+(kz_eval_masked_fwd/bwd) on CUDA and in plain PyTorch elsewhere.
 
 Models: ``ActorCritic`` (keisei/core/neural_network.py:10-29) and ``ActorCriticResTower`` with optional
 squeeze-excitation (keisei/training/models/resnet_tower.py:15-84).  Parameter names match the reference so that
@@ -17,7 +18,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .. import rl
+from .. import nn_ops, rl
 
 _EPS = torch.finfo(torch.float32).eps
 _sample_counter = itertools.count()
@@ -109,7 +110,10 @@ class ActorCritic(BaseActorCriticModel):
         self.value_head = nn.Linear(16 * 81, 1)
 
     def forward(self, x):
-        x = self.flatten(self.relu(self.conv(x)))
+        if nn_ops.obs_conv_applicable(self.conv, x):  # bf16 autocast on CUDA: fused input layer (csrc/kz_nn.cu)
+            x = self.flatten(nn_ops.obs_conv(x, self.conv.weight, self.conv.bias, relu=True))
+        else:
+            x = self.flatten(self.relu(self.conv(x)))
         return padded_linear(x, self.policy_head), self.value_head(x)
 
 

@@ -1111,6 +1111,9 @@ int cuda_fail(cudaError_t e) {
   snprintf(t_cuda_err, sizeof t_cuda_err, "%s", cudaGetErrorString(e));
   return KZ_E_CUDA;
 }
+}  // namespace
+int kz_cuda_fail(cudaError_t e) { return cuda_fail(e); }  // shared with kz_rl.cu / kz_nn.cu: one kz_last_cuda_error
+namespace {
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return cuda_fail(_e); } while (0)
 
 int g_sm_count = 0;

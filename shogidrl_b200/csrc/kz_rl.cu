@@ -11,13 +11,11 @@
 
 #define FULL 0xffffffffu
 
+int kz_cuda_fail(cudaError_t e);  // kz_engine.cu: records the message for kz_last_cuda_error
+
 namespace {
 
-thread_local char t_err[256] = "";
-int fail(cudaError_t e) {
-  snprintf(t_err, sizeof t_err, "%s", cudaGetErrorString(e));
-  return KZ_E_CUDA;
-}
+inline int fail(cudaError_t e) { return kz_cuda_fail(e); }
 
 __device__ __forceinline__ float ld_logit(const void* row, int i, int bf16) {
   return bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(row)[i]) : reinterpret_cast<const float*>(row)[i];

@@ -212,3 +212,69 @@ def test_dense_mask_sampling_law():
     freq = torch.bincount(act, minlength=A).float() / n
     sigma = torch.sqrt(probs[0, top] * (1 - probs[0, top]) / n)
     assert bool(((freq[top] - probs[0, top]).abs() < 5 * sigma + 1e-6).all())
+
+
+def _conv_case(n, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    obs = torch.rand(n, 46, 9, 9, generator=g)
+    obs[:, :28] = (obs[:, :28] < 0.05).float()          # piece planes are 0/1, like real observations
+    w = torch.randn(16, 46, 3, 3, generator=g) * 0.05
+    b = torch.randn(16, generator=g) * 0.1
+    return obs.cuda(), w.cuda(), b.cuda()
+
+
+@pytest.mark.parametrize("n", [1, 37, 1500])
+@pytest.mark.parametrize("relu", [True, False])
+def test_obs_conv_forward_and_weight_gradient(n, relu):
+    """kz_obs_conv_fwd / kz_obs_conv_wgrad against an fp64 convolution of the bf16-rounded operands (what bf16
+    autocast feeds cuDNN): outputs within one bf16 rounding, weight / bias gradients within 1e-4 of their scale."""
+    from shogidrl_b200 import nn_ops
+    import torch.nn.functional as F
+    obs, w, b = _conv_case(n, seed=n)
+    wp, bp = w.clone().requires_grad_(), b.clone().requires_grad_()
+    y = nn_ops.obs_conv(obs, wp, bp, relu=relu)
+    assert y.dtype == torch.bfloat16 and y.shape == (n, 16, 9, 9)
+    xd, wd, bd = obs.bfloat16().double(), w.bfloat16().double().requires_grad_(), b.bfloat16().double().requires_grad_()
+    pre = F.conv2d(xd, wd, bd, padding=1)
+    ref = pre.relu() if relu else pre
+    err = (y.double() - ref).abs()
+    assert bool((err <= ref.abs() * 2.0 ** -8 + 1e-3).all()), float(err.max())
+    g = torch.Generator(device="cpu").manual_seed(5)
+    dy = torch.randn(n, 16, 9, 9, generator=g).cuda()
+    for dyk in (dy.bfloat16(), dy):
+        wp.grad = bp.grad = None
+        y2 = nn_ops.obs_conv(obs, wp, bp, relu=relu)
+        y2.backward(dyk.to(y2.dtype) if dyk.dtype == torch.bfloat16 else dyk)
+        # reference: the ReLU gate of the kernel's own (bf16) output, dy rounded to bf16
+        gate = (y2.double() > 0) if relu else torch.ones_like(pre, dtype=torch.bool)
+        dyd = torch.where(gate, dyk.bfloat16().double(), torch.zeros((), dtype=torch.float64, device="cuda"))
+        gw, gb = torch.autograd.grad(pre, (wd, bd), dyd, retain_graph=True)
+        assert float((wp.grad.double() - gw).abs().max()) <= 1e-4 * float(gw.abs().max()) + 1e-6
+        assert float((bp.grad.double() - gb).abs().max()) <= 1e-4 * float(gb.abs().max()) + 1e-6
+
+
+def test_actor_critic_uses_fused_input_layer_under_autocast():
+    """Default CNN under bf16 autocast: fused input layer vs the cuDNN path -- same logits/values within bf16
+    noise, same parameter gradients within 2 %."""
+    from shogidrl_b200.core import ActorCritic
+    from shogidrl_b200 import nn_ops
+    torch.manual_seed(0)
+    model = ActorCritic(46, A).cuda()
+    obs, _, _ = _conv_case(64, seed=3)
+    outs = []
+    for fused in (True, False):
+        model.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            assert nn_ops.obs_conv_applicable(model.conv, obs)
+            if fused:
+                logits, value = model(obs)
+            else:
+                x = model.flatten(model.relu(model.conv(obs)))
+                logits, value = model.policy_head(x), model.value_head(x)
+        (logits.float().square().mean() + value.float().square().mean()).backward()
+        outs.append((logits.float().detach().clone(), value.float().detach().clone(), model.conv.weight.grad.clone(),
+                     model.conv.bias.grad.clone()))
+    (l1, v1, gw1, gb1), (l2, v2, gw2, gb2) = outs
+    assert torch.allclose(l1, l2, rtol=2e-2, atol=2e-2) and torch.allclose(v1, v2, rtol=2e-2, atol=2e-2)
+    assert float((gw1 - gw2).abs().max()) <= 2e-2 * float(gw2.abs().max())
+    assert float((gb1 - gb2).abs().max()) <= 2e-2 * float(gb2.abs().max())
