@@ -169,15 +169,17 @@ int kz_eval_masked_bwd(const void* logits, int logits_bf16, int64_t ld, const ui
 /* ---- observation input layer of the default policy/value network (keisei/core/neural_network.py:14-28:
  * nn.Conv2d(46, 16, kernel_size=3, padding=1) [+ ReLU], run under bf16 autocast by ppo_agent.py:323) ----
  * kz_obs_conv_fwd: out[n][16][9][9] (bf16) = [relu](conv3x3(obs fp32 [n][46][9][9], weight fp32 [16][46][3][3]) + bias),
- * operands rounded to bf16, fp32 accumulation (what autocast computes).  cout must be 16.
+ * operands rounded to bf16, fp32 accumulation (what autocast computes).  cout must be 16.  obs_rows (int64 [n] or
+ * NULL): board b is read from row obs_rows[b] of the observation storage -- the minibatch gather of
+ * ppo_agent.py:300-309 done in place.
  * kz_obs_conv_wgrad: dweight [16][46][3][3] / dbias [16] (fp32, overwritten) from dout [n][16][9][9] (bf16 or fp32);
  * y_bf16 = the saved forward output when the forward applied ReLU (its backward is fused), else NULL.
  * workspace: ctas * 16 * 432 floats with ctas = kz_obs_conv_wgrad_ctas(n); deterministic (no atomics). */
-int kz_obs_conv_fwd(const float* obs, const float* weight, const float* bias, int cout, int n, int relu, void* out_bf16,
-                    void* stream);
+int kz_obs_conv_fwd(const float* obs, const int64_t* obs_rows, const float* weight, const float* bias, int cout, int n,
+                    int relu, void* out_bf16, void* stream);
 int kz_obs_conv_wgrad_ctas(int n);
-int kz_obs_conv_wgrad(const float* obs, const void* y_bf16, const void* dout, int dout_bf16, int cout, int n,
-                      float* workspace, int ctas, float* dweight, float* dbias, void* stream);
+int kz_obs_conv_wgrad(const float* obs, const int64_t* obs_rows, const void* y_bf16, const void* dout, int dout_bf16,
+                      int cout, int n, float* workspace, int ctas, float* dweight, float* dbias, void* stream);
 
 #ifdef __cplusplus
 }

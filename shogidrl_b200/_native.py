@@ -63,9 +63,9 @@ def lib() -> C.CDLL:
     L.kz_gae_exact.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp, vp]
     L.kz_eval_masked_fwd.argtypes = [vp, i32, i64, vp, i64, vp, vp, i32, vp, vp, vp, vp]
     L.kz_eval_masked_bwd.argtypes = [vp, i32, i64, vp, i64, vp, vp, i32, vp, vp, vp, vp, i64, vp]
-    L.kz_obs_conv_fwd.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
+    L.kz_obs_conv_fwd.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp]
     L.kz_obs_conv_wgrad_ctas.argtypes = [i32]
-    L.kz_obs_conv_wgrad.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, vp, vp, vp]
+    L.kz_obs_conv_wgrad.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, i32, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("kz_last_cuda_error",):

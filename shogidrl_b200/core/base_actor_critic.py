@@ -109,12 +109,24 @@ class ActorCritic(BaseActorCriticModel):
         self.policy_head = nn.Linear(16 * 81, num_actions_total)
         self.value_head = nn.Linear(16 * 81, 1)
 
-    def forward(self, x):
+    fused_minibatch = True  # forward(obs_store, rows=..., actions=..., legal_mask=...) evaluates a PPO minibatch
+
+    def forward(self, x, rows=None, actions=None, legal_mask=None, mask_rows=None):
+        """``forward(x)`` -> (logits, value) as in the reference.  The PPO update calls (through the DDP wrapper when
+        there is one) ``forward(obs_store, rows=mb, actions=a, legal_mask=mask_store, mask_rows=mb)`` and gets
+        (log_probs, entropy, value) of the minibatch: observations and masks are read in place through the row
+        indices, the input layer and the policy head + masked evaluation each run as one fused node."""
         if nn_ops.obs_conv_applicable(self.conv, x):  # bf16 autocast on CUDA: fused input layer (csrc/kz_nn.cu)
-            x = self.flatten(nn_ops.obs_conv(x, self.conv.weight, self.conv.bias, relu=True))
+            h = self.flatten(nn_ops.obs_conv(x, self.conv.weight, self.conv.bias, relu=True, rows=rows))
         else:
-            x = self.flatten(self.relu(self.conv(x)))
-        return padded_linear(x, self.policy_head), self.value_head(x)
+            h = self.flatten(self.relu(self.conv(x if rows is None else x[rows])))
+        if actions is None:
+            return padded_linear(h, self.policy_head), self.value_head(h)
+        value = self.value_head(h).squeeze(-1)
+        if h.is_cuda and h.dtype == torch.bfloat16 and legal_mask is not None:
+            log_probs, entropy = nn_ops.policy_head_evaluate(h, self.policy_head, legal_mask, actions, mask_rows)
+            return log_probs, entropy, value
+        return self.evaluate_from_logits(padded_linear(h, self.policy_head), value, actions, legal_mask, mask_rows)
 
 
 class SqueezeExcitation(nn.Module):

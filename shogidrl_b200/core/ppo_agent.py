@@ -57,11 +57,17 @@ class PPOAgent:
         self.num_actions_total = self.policy_output_mapper.get_total_actions()
         tr = config.training
         weight_decay = getattr(tr, "weight_decay", 0.0)
+        # capturable: step counters live on the device, so a whole minibatch update can sit in one CUDA graph
+        adam = dict(weight_decay=weight_decay, capturable=self.device.type == "cuda")
         try:
-            self.optimizer = torch.optim.Adam(self.model.parameters(), lr=tr.learning_rate, weight_decay=weight_decay)
+            self.optimizer = torch.optim.Adam(self.model.parameters(), lr=tr.learning_rate, **adam)
         except Exception as e:  # same fallback as the reference (ppo_agent.py:72-80)
             _log("ERROR", f"Could not initialize optimizer with lr={tr.learning_rate}, using default lr=1e-3: {e}")
-            self.optimizer = torch.optim.Adam(self.model.parameters(), lr=1e-3, weight_decay=weight_decay)
+            self.optimizer = torch.optim.Adam(self.model.parameters(), lr=1e-3, **adam)
+        self.cuda_graph_update = bool(getattr(tr, "cuda_graph_update", True))
+        self._graph = None          # captured minibatch update (forward, losses, backward, clip, Adam)
+        self._graph_key = None
+        self._graph_warm = 0
         self.gamma = tr.gamma
         self.clip_epsilon = tr.clip_epsilon
         self.value_loss_coeff = tr.value_loss_coeff
@@ -148,58 +154,123 @@ class PPOAgent:
         if self.normalize_advantages:
             adv_b = self._normalize(adv_b)
         n = obs_b.shape[0]
-        indices = np.arange(n)
-        sums = torch.zeros(5, device=d)  # policy, value, entropy-loss, kl, clip fraction
+        self._sums = torch.zeros(5, device=d) if getattr(self, "_sums", None) is None else self._sums.zero_()
+        if getattr(self, "_gn", None) is None:
+            self._gn = torch.zeros((), device=d)
         updates = 0
+        in_place = (getattr(getattr(self.model, "module", self.model), "fused_minibatch", False)
+                    and not self._is_obs_scaler() and d.type == "cuda")
+        S = {"obs": obs_b, "act": act_b, "oldlp": oldlp_b, "oldv": oldv_b, "adv": adv_b, "ret": ret_b, "mask": mask_b}
+        graphed = (in_place and self.cuda_graph_update and getattr(self, "_ddp", None) is None and self.scheduler is None
+                   and n >= self.minibatch_size)
+        if graphed:
+            S = self._static_batch(S)
         for _ in range(self.ppo_epochs):
-            self._rng.shuffle(indices)
+            # minibatch order drawn on the device (the reference shuffles a numpy index array, ppo_agent.py:298)
+            indices = torch.randperm(n, device=d, generator=self._device_generator())
             for start in range(0, n, self.minibatch_size):
-                mb = torch.as_tensor(indices[start:start + self.minibatch_size], device=d)
-                with self._autocast():
-                    logits, values = self._train_forward(self._scale(obs_b[mb]))
-                    # masks are read in place from the rollout storage through the minibatch indices (no gather)
-                    new_lp, entropy, new_v = type(self.model).evaluate_from_logits(logits, values, act_b[mb], mask_b,
-                                                                                   mask_rows=mb)
-                new_v = new_v.float()
-                ratio = torch.exp(new_lp - oldlp_b[mb])
-                adv = adv_b[mb]
-                policy_loss = -torch.min(ratio * adv, torch.clamp(ratio, 1 - self.clip_epsilon, 1 + self.clip_epsilon) * adv).mean()
-                if self.enable_value_clipping:
-                    clipped = oldv_b[mb] + torch.clamp(new_v - oldv_b[mb], -self.clip_epsilon, self.clip_epsilon)
-                    value_loss = torch.max(F.mse_loss(new_v.squeeze(), ret_b[mb].squeeze()),
-                                           F.mse_loss(clipped.squeeze(), ret_b[mb].squeeze()))
+                mb = indices[start:start + self.minibatch_size]
+                if graphed and mb.shape[0] == self.minibatch_size:
+                    self._graphed_update(S, mb)
                 else:
-                    value_loss = F.mse_loss(new_v.squeeze(), ret_b[mb].squeeze())
-                entropy_loss = -entropy.mean()
-                loss = policy_loss + self.value_loss_coeff * value_loss + self.entropy_coef * entropy_loss
-                self.optimizer.zero_grad(set_to_none=True)
-                loss.backward()  # under DistributedDataParallel the gradient all-reduce (NCCL) fires here
-                gn = torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.gradient_clip_max_norm)
-                self.optimizer.step()
+                    self._minibatch_update(S, mb, in_place)
                 if self.scheduler is not None and self.lr_schedule_step_on == "update":
                     self.scheduler.step()
-                with torch.no_grad():
-                    sums += torch.stack([policy_loss, value_loss, entropy_loss, (oldlp_b[mb] - new_lp).mean(),
-                                         ((ratio - 1.0).abs() > self.clip_epsilon).float().mean()]).detach()
-                    self._gn = gn
                 updates += 1
         if self.scheduler is not None and self.lr_schedule_step_on == "epoch":
             self.scheduler.step()
-        avg = (sums / max(1, updates)).tolist()  # one host synchronisation per learn() instead of 5 per minibatch
+        avg = (self._sums / max(1, updates)).tolist()  # one host synchronisation per learn() instead of 5 per minibatch
         self.last_gradient_norm = float(self._gn) if updates else 0.0
         self.last_kl_div = avg[3]
         return {"ppo/policy_loss": avg[0], "ppo/value_loss": avg[1], "ppo/entropy": avg[2],
                 "ppo/kl_divergence_approx": avg[3], "ppo/clip_fraction": avg[4],
                 "ppo/learning_rate": self.optimizer.param_groups[0]["lr"]}
 
+    def _minibatch_update(self, S: Dict[str, torch.Tensor], mb: torch.Tensor, in_place: bool) -> None:
+        """One clipped-surrogate update (ppo_agent.py:300-420) entirely on the device: no host synchronisation, so
+        the same code runs eagerly or under CUDA-graph capture."""
+        with self._autocast():
+            if in_place:
+                # observations and masks are read in place from the rollout storage through the minibatch indices;
+                # input layer and policy head + masked evaluation are fused nodes (nn_ops.py)
+                new_lp, entropy, new_v = self._train_forward(S["obs"], rows=mb, actions=S["act"][mb], legal_mask=S["mask"],
+                                                             mask_rows=mb)
+            else:
+                logits, values = self._train_forward(self._scale(S["obs"][mb]))
+                new_lp, entropy, new_v = type(self.model).evaluate_from_logits(logits, values, S["act"][mb], S["mask"],
+                                                                               mask_rows=mb)
+        new_v = new_v.float()
+        old_lp, adv, ret = S["oldlp"][mb], S["adv"][mb], S["ret"][mb]
+        ratio = torch.exp(new_lp - old_lp)
+        policy_loss = -torch.min(ratio * adv, torch.clamp(ratio, 1 - self.clip_epsilon, 1 + self.clip_epsilon) * adv).mean()
+        if self.enable_value_clipping:
+            old_v = S["oldv"][mb]
+            clipped = old_v + torch.clamp(new_v - old_v, -self.clip_epsilon, self.clip_epsilon)
+            value_loss = torch.max(F.mse_loss(new_v.squeeze(), ret.squeeze()), F.mse_loss(clipped.squeeze(), ret.squeeze()))
+        else:
+            value_loss = F.mse_loss(new_v.squeeze(), ret.squeeze())
+        entropy_loss = -entropy.mean()
+        loss = policy_loss + self.value_loss_coeff * value_loss + self.entropy_coef * entropy_loss
+        self.optimizer.zero_grad(set_to_none=True)
+        loss.backward()  # under DistributedDataParallel the gradient all-reduce (NCCL) fires here
+        gn = torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.gradient_clip_max_norm)
+        self.optimizer.step()
+        with torch.no_grad():
+            self._sums += torch.stack([policy_loss, value_loss, entropy_loss, (old_lp - new_lp).mean(),
+                                       ((ratio - 1.0).abs() > self.clip_epsilon).float().mean()]).detach()
+            self._gn.copy_(gn)
+
+    def _static_batch(self, S: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Pin the batch to fixed addresses for graph replay: the rollout storage already is; the normalised
+        advantages are a fresh tensor per learn() and are copied into a persistent one.  A different storage (or
+        size) invalidates the captured graph."""
+        if getattr(self, "_static_adv", None) is None or self._static_adv.shape != S["adv"].shape:
+            self._static_adv = torch.empty_like(S["adv"])
+        self._static_adv.copy_(S["adv"])
+        S = dict(S, adv=self._static_adv)
+        key = tuple((k, v.data_ptr(), tuple(v.shape), tuple(v.stride())) for k, v in sorted(S.items())) + (self.minibatch_size,)
+        if key != self._graph_key:
+            self._graph, self._graph_key, self._graph_warm = None, key, 0
+            self._static_mb = torch.empty(self.minibatch_size, dtype=torch.int64, device=self.device)
+        return S
+
+    def _graphed_update(self, S: Dict[str, torch.Tensor], mb: torch.Tensor) -> None:
+        """Launch-bound inner loop -> one CUDA graph per minibatch update (~60 kernels, 2.4 ms of device time
+        against 6.6 ms of eager launch overhead on B200).  The first three minibatches run eagerly on a side
+        stream (allocator / cuBLAS warm-up, as torch.cuda.graphs requires), the fourth is captured, the rest replay."""
+        self._static_mb.copy_(mb)
+        if self._graph is not None:
+            self._graph.replay()
+            return
+        if self._graph_warm < 3:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                self._minibatch_update(S, self._static_mb, True)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            self._graph_warm += 1
+            return
+        graph = torch.cuda.CUDAGraph()
+        self.optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            self._minibatch_update(S, self._static_mb, True)
+        self._graph = graph
+        graph.replay()
+
     def enable_ddp(self) -> None:
         """Wrap the model for the update when torch.distributed is initialised (gradient all-reduce over NCCL)."""
         from ..training import distributed as kd
         self._ddp = kd.wrap_ddp(self.model, self.device)
 
-    def _train_forward(self, obs: torch.Tensor):
+    def _train_forward(self, obs: torch.Tensor, **kwargs):
         ddp = getattr(self, "_ddp", None)
-        return (ddp if ddp is not None else self.model)(obs)
+        return (ddp if ddp is not None else self.model)(obs, **kwargs)
+
+    def _device_generator(self) -> torch.Generator:
+        if getattr(self, "_gen", None) is None:
+            self._gen = torch.Generator(device=self.device)
+            self._gen.manual_seed(int(self._rng.integers(0, 2 ** 62)))
+        return self._gen
 
     def _normalize(self, adv: torch.Tensor) -> torch.Tensor:
         """Whole-buffer normalisation (ppo_agent.py:276-282: unbiased std, skipped for tiny std / single sample).

@@ -97,7 +97,9 @@ __device__ __forceinline__ void store_board(__nv_bfloat16* xs, const BoardRegs<N
 }
 
 // ---- forward: 4 warps, warp w owns column tiles w, w + 4, w + 8 (8 board squares each; 11 tiles cover 81) ----
-__global__ void __launch_bounds__(128) kz_obs_conv_fwd_kernel(const float* __restrict__ obs, const float* __restrict__ w,
+__global__ void __launch_bounds__(128) kz_obs_conv_fwd_kernel(const float* __restrict__ obs,
+                                                              const long long* __restrict__ rows,
+                                                              const float* __restrict__ w,
                                                               const float* __restrict__ bias, int n, int relu,
                                                               __nv_bfloat16* __restrict__ out) {
   __shared__ __align__(16) __nv_bfloat16 ws[COUT * WS_STRIDE];
@@ -126,12 +128,13 @@ __global__ void __launch_bounds__(128) kz_obs_conv_fwd_kernel(const float* __res
   }
   const uint32_t xs_b = smem_u32(xs) + ((lane >> 3) & 1) * 16;
   BoardRegs<128> regs;
-  if (blockIdx.x < n) load_board<128>(regs, obs + (size_t)blockIdx.x * CIN * 81, tid);
+  auto board = [&](int b) { return obs + (size_t)(rows ? rows[b] : b) * CIN * 81; };  // in-place minibatch gather
+  if (blockIdx.x < n) load_board<128>(regs, board(blockIdx.x), tid);
   for (int b = blockIdx.x; b < n; b += gridDim.x) {
     __syncthreads();  // previous board's ys copied out, xs free
     store_board<128>(xs, regs, tid);
     __syncthreads();
-    if (b + gridDim.x < n) load_board<128>(regs, obs + (size_t)(b + gridDim.x) * CIN * 81, tid);  // next board in flight
+    if (b + gridDim.x < n) load_board<128>(regs, board(b + gridDim.x), tid);  // next board in flight
     float acc[3][4];
 #pragma unroll
     for (int j = 0; j < 3; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
@@ -171,6 +174,7 @@ __global__ void __launch_bounds__(128) kz_obs_conv_fwd_kernel(const float* __res
 
 // ---- weight gradient: 9 warps, warp t owns tap t: dW[o][t][c] += sum_xy dy[o][xy] * tile[row(xy) + off(t)][c] ----
 __global__ void __launch_bounds__(288) kz_obs_conv_wgrad_kernel(const float* __restrict__ obs,
+                                                                const long long* __restrict__ rows,
                                                                 const __nv_bfloat16* __restrict__ y, const void* dout,
                                                                 int dout_bf16, int n, float* __restrict__ part) {
   __shared__ __align__(16) __nv_bfloat16 xs[XS_ROWS * XS_STRIDE];
@@ -200,8 +204,9 @@ __global__ void __launch_bounds__(288) kz_obs_conv_wgrad_kernel(const float* __r
       }
     }
   };
+  auto board = [&](int b) { return obs + (size_t)(rows ? rows[b] : b) * CIN * 81; };
   if (blockIdx.x < n) {
-    load_board<288>(regs, obs + (size_t)blockIdx.x * CIN * 81, tid);
+    load_board<288>(regs, board(blockIdx.x), tid);
     load_dy(blockIdx.x);
   }
   for (int b = blockIdx.x; b < n; b += gridDim.x) {
@@ -217,7 +222,7 @@ __global__ void __launch_bounds__(288) kz_obs_conv_wgrad_kernel(const float* __r
     }
     __syncthreads();
     if (b + gridDim.x < n) {  // next board in flight during the products
-      load_board<288>(regs, obs + (size_t)(b + gridDim.x) * CIN * 81, tid);
+      load_board<288>(regs, board(b + gridDim.x), tid);
       load_dy(b + gridDim.x);
     }
 #pragma unroll
@@ -275,12 +280,12 @@ int resident_ctas(K kernel, int threads) {
 
 extern "C" {
 
-int kz_obs_conv_fwd(const float* obs, const float* weight, const float* bias, int cout, int n, int relu, void* out_bf16,
-                    void* stream) {
+int kz_obs_conv_fwd(const float* obs, const int64_t* obs_rows, const float* weight, const float* bias, int cout, int n,
+                    int relu, void* out_bf16, void* stream) {
   if (!obs || !weight || !out_bf16 || n <= 0 || cout != COUT) return KZ_E_ARG;
   static const int resident = resident_ctas(kz_obs_conv_fwd_kernel, 128);
   kz_obs_conv_fwd_kernel<<<n < resident ? n : resident, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      obs, weight, bias, n, relu, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+      obs, reinterpret_cast<const long long*>(obs_rows), weight, bias, n, relu, reinterpret_cast<__nv_bfloat16*>(out_bf16));
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? KZ_OK : fail(e);
 }
@@ -290,12 +295,12 @@ int kz_obs_conv_wgrad_ctas(int n) {
   return n < resident ? (n > 0 ? n : 1) : resident;
 }
 
-int kz_obs_conv_wgrad(const float* obs, const void* y_bf16, const void* dout, int dout_bf16, int cout, int n,
-                      float* workspace, int ctas, float* dweight, float* dbias, void* stream) {
+int kz_obs_conv_wgrad(const float* obs, const int64_t* obs_rows, const void* y_bf16, const void* dout, int dout_bf16,
+                      int cout, int n, float* workspace, int ctas, float* dweight, float* dbias, void* stream) {
   if (!obs || !dout || !workspace || !dweight || n <= 0 || cout != COUT || ctas <= 0 || ctas > n) return KZ_E_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  kz_obs_conv_wgrad_kernel<<<ctas, 288, 0, st>>>(obs, reinterpret_cast<const __nv_bfloat16*>(y_bf16), dout, dout_bf16, n,
-                                                 workspace);
+  kz_obs_conv_wgrad_kernel<<<ctas, 288, 0, st>>>(obs, reinterpret_cast<const long long*>(obs_rows),
+                                                 reinterpret_cast<const __nv_bfloat16*>(y_bf16), dout, dout_bf16, n, workspace);
   kz_obs_conv_wgrad_reduce_kernel<<<(COUT * KTOT + 127) / 128, 128, 0, st>>>(workspace, ctas, dweight, dbias);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? KZ_OK : fail(e);

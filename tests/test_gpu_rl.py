@@ -278,3 +278,40 @@ def test_actor_critic_uses_fused_input_layer_under_autocast():
     assert torch.allclose(l1, l2, rtol=2e-2, atol=2e-2) and torch.allclose(v1, v2, rtol=2e-2, atol=2e-2)
     assert float((gw1 - gw2).abs().max()) <= 2e-2 * float(gw2.abs().max())
     assert float((gb1 - gb2).abs().max()) <= 2e-2 * float(gb2.abs().max())
+
+
+def test_fused_minibatch_forward_matches_unfused_path():
+    """ActorCritic.forward(obs_store, rows=, actions=, legal_mask=, mask_rows=) -- the PPO update's in-place
+    minibatch evaluation -- against gather + forward + evaluate_from_logits: same log-probs / entropy / value and
+    the same gradients for every parameter (bf16 tolerances)."""
+    from shogidrl_b200.core import ActorCritic
+    torch.manual_seed(1)
+    dev = torch.device("cuda:0")
+    model = ActorCritic(46, A).to(dev)
+    store_n, n = 300, 128
+    obs, _, _ = _conv_case(store_n, seed=8)
+    _, mask = _random_case(store_n, dev, seed=12)
+    mask_store = torch.zeros(store_n, 13536, dtype=torch.uint8, device=dev)
+    mask_store[:, :A] = mask
+    rows = torch.randperm(store_n, device=dev)[:n]
+    actions = torch.stack([torch.nonzero(mask[i])[0, 0] for i in rows.tolist()])
+    w_lp, w_ent, w_v = torch.randn(n, device=dev), torch.randn(n, device=dev) * 0.1, torch.randn(n, device=dev)
+    results = []
+    for fused in (True, False):
+        model.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            if fused:
+                lp, ent, v = model(obs, rows=rows, actions=actions, legal_mask=mask_store[:, :A], mask_rows=rows)
+            else:
+                x = model.flatten(model.relu(model.conv(obs[rows])))
+                logits, value = model.policy_head(x), model.value_head(x)
+                lp, ent, v = ActorCritic.evaluate_from_logits(logits, value, actions, mask[rows])
+        ((lp * w_lp).sum() + (ent * w_ent).sum() + (v.float() * w_v).sum()).backward()
+        results.append((lp.detach().clone(), ent.detach().clone(), v.float().detach().clone(),
+                        {k: p.grad.clone() for k, p in model.named_parameters()}))
+    (lp1, e1, v1, g1), (lp2, e2, v2, g2) = results
+    assert torch.allclose(lp1, lp2, rtol=2e-2, atol=2e-2), float((lp1 - lp2).abs().max())
+    assert torch.allclose(e1, e2, rtol=2e-2, atol=2e-2) and torch.allclose(v1, v2, rtol=2e-2, atol=2e-2)
+    for k in g1:
+        scale = float(g2[k].abs().max())
+        assert float((g1[k] - g2[k]).abs().max()) <= 3e-2 * scale + 1e-6, (k, float((g1[k] - g2[k]).abs().max()), scale)
