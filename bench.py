@@ -371,7 +371,10 @@ def run_ppo(args):
                            "rollout_samples_per_s": samples / (roll_ms * 1e-3), "update_samples_per_s": samples / (upd_ms * 1e-3),
                            "rollout_ms": roll_ms / args.steps, "update_ms": upd_ms / args.steps,
                            "last_metrics": {k: float(v) for k, v in m.items()}},
-                "gpu_launches": args.steps * T}
+                # own kernels per epoch: rollout steps (kz_step, kz_sample_masked, + kz_obs_conv_fwd for the CNN), kz_gae,
+                # and per minibatch update kz_eval_masked_fwd/bwd (+ kz_obs_conv_fwd and the two wgrad kernels)
+                "gpu_launches": args.steps * (T * (3 if args.ppo_model == "cnn" else 2) + 1
+                                              + -(-N * T // mb) * args.ppo_epochs * (5 if args.ppo_model == "cnn" else 2))}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -31,4 +31,9 @@ t = time.perf_counter(); agent.learn(buf); torch.cuda.synchronize(); dt = time.p
 print(f"learn(): {dt*1e3:.1f} ms for 4 minibatch updates -> {dt*1e3/4:.1f} ms per update")
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     agent.learn(buf); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=22, max_name_column_width=60))
+rows = [(e.self_device_time_total / 4, e.count // 4 if e.count >= 4 else e.count, e.key) for e in prof.key_averages() if e.self_device_time_total > 0]
+rows.sort(reverse=True)
+print("device time per minibatch update (us), launches, kernel")
+for t, c, k in rows[:40]:
+    print(f"{t:9.1f} {c:4d}  {k[:150]}")
+print(f"total {sum(r[0] for r in rows):.0f} us")
