@@ -397,3 +397,55 @@ def test_long_game_stress_mix():
     assert np.array_equal(reasons[:, :2 * n_each], ref["reasons"])
     hist = np.bincount(reasons[:, :2 * n_each].ravel(), minlength=5)
     assert hist[1] > 0 and hist[3] > 0  # checkmates and max-move truncations both occur
+
+
+def test_full_size_stress_properties():
+    """BASELINE config 5 at its full per-GPU size (262,144 games, 500-ply repetition tables): a mix of start
+    positions, drop-heavy endgames and sennichite cycles stepped with random legal play under max-move truncation.
+    The oracle cannot follow at this size, so the check is through size-independent properties every step:
+    no error bits; piece conservation (board + hands) per game between resets; the mask row's popcount equals the
+    kernel's legal count and the pre-selected next action is legal; move counters never pass max_moves; a reset
+    game is exactly the start position; and at the end kz_refresh reproduces the obs / mask that kz_step wrote."""
+    from shogidrl_b200 import VecShogiEnv
+    dev = torch.device("cuda:0")
+    n, max_moves, T = 262144, 96, 40
+    n_each = 2048
+    start = orc.OracleGame().export()
+    eg = _random_endgames(n_each, 123)
+    cyc = orc.parse_sfen("4k4/9/9/9/9/R8/9/9/4K4 b - 1")
+    reps = n // (4 * n_each)
+    boards = np.concatenate([np.tile(start[0], (2 * n_each, 1)), eg[0], np.tile(cyc[0], (n_each, 1))] * reps)
+    hands = np.concatenate([np.tile(start[1], (2 * n_each, 1)), eg[1], np.tile(cyc[1], (n_each, 1))] * reps)
+    sides = np.concatenate([np.zeros(2 * n_each, np.uint8), eg[2], np.zeros(n_each, np.uint8)] * reps)
+    rng = np.random.default_rng(5)
+    mcs = rng.integers(0, max_moves - 8, n).astype(np.int32)      # staggered move counters: truncations at every step
+    assert boards.shape[0] == n
+    env = VecShogiEnv(n, max_moves_per_game=max_moves, device=dev, seed=99, auto_reset=True)
+    env.load_positions(boards, hands, sides, mcs, eval_termination=False)
+    env.refresh(random_actions=True)
+    start_b = torch.as_tensor(start[0], device=dev)
+    b0, h0, _ = env.export()
+    pieces = (b0 != 0).sum(1) + h0.sum(1, dtype=torch.int64)
+    reasons = torch.zeros(5, dtype=torch.int64, device=dev)
+    acts = [env.next_actions.clone(), torch.empty_like(env.next_actions)]
+    for t in range(T):
+        a = acts[t & 1]
+        assert bool(env.mask.gather(1, a[:, None]).all())                      # pre-selected action is legal
+        out = env.step(a, random_actions=True, next_out=acts[(t + 1) & 1])
+        done = out["done"].bool()
+        reasons += torch.bincount(out["reason"].long(), minlength=5)
+        b, h, m = env.export()
+        now = (b != 0).sum(1) + h.sum(1, dtype=torch.int64)
+        assert bool((now[~done] == pieces[~done]).all())                       # conservation while a game runs
+        assert bool((b[done] == start_b).all()) and bool((h[done] == 0).all()) and bool((m[done, 1] == 0).all())
+        assert bool((m[done, 0] == 0).all())                                   # reset games: start position, Black to move
+        pieces = torch.where(done, torch.full_like(pieces, 40), pieces)
+        assert int(m[:, 1].max()) < max_moves and int(env.errors().abs().sum()) == 0
+        if t % 8 == 0 or t == T - 1:
+            assert torch.equal(env.mask.sum(1, dtype=torch.int32), out["legal_count"].int())
+            assert int(out["legal_count"].min()) > 0                           # live games always have a legal move
+    obs_k, mask_k = env.obs.clone(), env.mask.clone()
+    env.refresh()
+    assert torch.equal(env.obs, obs_k) and torch.equal(env.mask, mask_k)       # refresh == what the step kernel wrote
+    r = reasons.tolist()
+    assert r[1] > 0 and r[3] > 0 and r[4] > 0, r                               # checkmates, truncations and sennichite all occur
