@@ -377,7 +377,19 @@ def run_ppo(args):
                                               + -(-N * T // mb) * args.ppo_epochs * (5 if args.ppo_model == "cnn" else 2))}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # the captured update graph holds NCCL work: release it before the process group goes away, and never let
+        # a stuck communicator teardown outlive the measurement
+        import gc
+        import threading
+        barrier()
+        tr.agent._graph = None
+        gc.collect()
+        torch.cuda.synchronize(dev)
+        killer = threading.Timer(30.0, lambda: os._exit(0))
+        killer.daemon = True
+        killer.start()
         dist.destroy_process_group()
+        killer.cancel()
     return 0
 
 

@@ -211,8 +211,14 @@ class PPOAgent:
             value_loss = F.mse_loss(new_v.squeeze(), ret.squeeze())
         entropy_loss = -entropy.mean()
         loss = policy_loss + self.value_loss_coeff * value_loss + self.entropy_coef * entropy_loss
+        grad_world = getattr(self, "_grad_world", 1)
+        if grad_world > 1:
+            loss = loss / grad_world  # the all-reduce below sums: mean gradient over ranks
         self.optimizer.zero_grad(set_to_none=True)
         loss.backward()  # under DistributedDataParallel the gradient all-reduce (NCCL) fires here
+        if grad_world > 1:
+            from ..training import distributed as kd
+            kd.all_reduce_grads(self.model.parameters())
         gn = torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.gradient_clip_max_norm)
         self.optimizer.step()
         with torch.no_grad():
@@ -258,9 +264,19 @@ class PPOAgent:
         graph.replay()
 
     def enable_ddp(self) -> None:
-        """Wrap the model for the update when torch.distributed is initialised (gradient all-reduce over NCCL)."""
+        """Data-parallel update when torch.distributed is initialised (the reference declares a ``ddp`` flag,
+        config_schema.py:81, but never wires it).  Models with the fused minibatch path average their gradients
+        with explicit all-reduces inside the update -- no wrapper hooks, so the update stays CUDA-graph capturable
+        (NCCL collectives are captured like kernels); other models are wrapped in DistributedDataParallel."""
         from ..training import distributed as kd
-        self._ddp = kd.wrap_ddp(self.model, self.device)
+        world = kd.world()[1]
+        if world == 1:
+            return
+        if getattr(self.model, "fused_minibatch", False):
+            kd.broadcast_module(self.model)
+            self._grad_world = world
+        else:
+            self._ddp = kd.wrap_ddp(self.model, self.device)
 
     def _train_forward(self, obs: torch.Tensor, **kwargs):
         ddp = getattr(self, "_ddp", None)

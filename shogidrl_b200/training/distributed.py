@@ -56,3 +56,20 @@ def wrap_ddp(model: torch.nn.Module, device: torch.device) -> torch.nn.Module:
         ids = [device.index] if device.type == "cuda" else None
         return torch.nn.parallel.DistributedDataParallel(model, device_ids=ids)
     return model
+
+
+def broadcast_module(module: torch.nn.Module, src: int = 0) -> None:
+    """Every rank starts from rank ``src``'s parameters and buffers (what the DDP constructor does)."""
+    if world()[1] > 1:
+        with torch.no_grad():
+            for t in list(module.parameters()) + list(module.buffers()):
+                dist.broadcast(t, src)
+
+
+def all_reduce_grads(params) -> None:
+    """Sum the gradients over ranks, one all-reduce per parameter (NCCL over NVLink on GPUs).  Issued on the
+    current stream, so a CUDA-graph capture of the update records them like kernels."""
+    if world()[1] > 1:
+        for p in params:
+            if p.grad is not None:
+                dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)

@@ -39,21 +39,36 @@ def _worker(rank, world, port, out):
         ref = (full - full.mean()) / full.std()
         assert torch.allclose(normed, ref[off:off + n], atol=1e-5)
         assert kd.reduce_max(1.0 + rank, "cpu") == float(world) and kd.reduce_sum(1.0, "cpu") == float(world)
-        # DDP: different data per rank, identical parameters after one update
+        # data-parallel update: different data per rank, identical parameters afterwards
         agent.enable_ddp()
         g = torch.Generator().manual_seed(100 + rank)
-        obs = torch.randn(8, 46, 9, 9, generator=g)
-        acts = torch.randint(0, 13527, (8,), generator=g)
-        logits, values = agent._train_forward(obs)
-        lp, ent, v = BaseActorCriticModel.evaluate_from_logits(logits, values, acts, None)
-        loss = -(lp.mean()) + 0.5 * (v ** 2).mean() - 0.01 * ent.mean()
-        agent.optimizer.zero_grad()
-        loss.backward()
-        agent.optimizer.step()
-        w = agent.model.value_head.weight.detach().clone()
-        gathered = [torch.zeros_like(w) for _ in range(world)]
-        dist.all_gather(gathered, w)
-        assert torch.equal(gathered[0], gathered[1])
+        # the fused-minibatch model takes the explicit all-reduce path (graph-capturable on GPUs) through learn()
+        assert getattr(agent, "_grad_world", 1) == world and getattr(agent, "_ddp", None) is None
+        B = 32
+        batch = {"obs": torch.randn(B, 46, 9, 9, generator=g), "actions": torch.randint(0, 13527, (B,), generator=g),
+                 "log_probs": torch.full((B,), -9.0), "values": torch.zeros(B), "advantages": torch.randn(B, generator=g),
+                 "returns": torch.randn(B, generator=g), "legal_masks": torch.ones(B, 13527, dtype=torch.bool)}
+
+        class Buf:
+            def get_batch(self):
+                return batch
+        metrics = agent.learn(Buf())
+        assert all(np.isfinite(v) for v in metrics.values())
+        for prm in agent.model.parameters():
+            gathered = [torch.zeros_like(prm) for _ in range(world)]
+            dist.all_gather(gathered, prm.detach().clone())
+            assert torch.equal(gathered[0], gathered[1])
+        # a model without the fused path is wrapped in DistributedDataParallel: same property through the wrapper
+        from shogidrl_b200.core.base_actor_critic import ActorCriticResTower
+        torch.manual_seed(rank)  # different initial weights per rank: the wrapper broadcasts rank 0's
+        agent2 = PPOAgent(ActorCriticResTower(46, 13527, tower_depth=1, tower_width=8), cfg, torch.device("cpu"))
+        agent2.enable_ddp()
+        assert isinstance(agent2._ddp, torch.nn.parallel.DistributedDataParallel)
+        agent2.learn(Buf())
+        for prm in agent2.model.parameters():
+            gathered = [torch.zeros_like(prm) for _ in range(world)]
+            dist.all_gather(gathered, prm.detach().clone())
+            assert torch.equal(gathered[0], gathered[1])
         out.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         out.put((rank, repr(e)))
