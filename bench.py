@@ -366,7 +366,7 @@ def run_ppo(args):
         line = {"metric": "PPO self-play samples/sec", "value": samples / (total_ms * 1e-3), "unit": "samples/s",
                 "n_gpus": world, "steps": args.steps, "warmup": 1, "ms_per_step": total_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": f"BASELINE config 3: PPO self-play, {args.ppo_model} policy-value net (bf16 autocast), {N} envs/GPU, "
+                "config": {"workload": f"BASELINE config {3 if args.ppo_model == 'cnn' else 4}: PPO self-play, {args.ppo_model} policy-value net (bf16 autocast), {N} envs/GPU, "
                                        f"T={T}, fused masked sampling + device GAE, ppo_epochs={args.ppo_epochs}, minibatch={mb}",
                            "rollout_samples_per_s": samples / (roll_ms * 1e-3), "update_samples_per_s": samples / (upd_ms * 1e-3),
                            "rollout_ms": roll_ms / args.steps, "update_ms": upd_ms / args.steps,
