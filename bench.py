@@ -157,7 +157,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -301,10 +301,28 @@ def run_product(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample(os.cpu_count() or 1)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+_JSON_OUT = None
+
+
+def isolate_stdout():
+    """Libraries write to fd 1 (NCCL prints its version line there): keep the real stdout for the one JSON line
+    and send everything else to stderr."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def run_ppo(args):
@@ -375,7 +393,7 @@ def run_ppo(args):
                 # and per minibatch update kz_eval_masked_fwd/bwd (+ kz_obs_conv_fwd and the two wgrad kernels)
                 "gpu_launches": args.steps * (T * (3 if args.ppo_model == "cnn" else 2) + 1
                                               + -(-N * T // mb) * args.ppo_epochs * (5 if args.ppo_model == "cnn" else 2))}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # the captured update graph holds NCCL work: release it before the process group goes away, and never let
         # a stuck communicator teardown outlive the measurement
@@ -418,6 +436,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    isolate_stdout()
     if args.workload == "ppo":
         return run_ppo(args)
     return run_product(args)
