@@ -166,6 +166,14 @@ int kz_eval_masked_bwd(const void* logits, int logits_bf16, int64_t ld, const ui
                        const int64_t* mask_rows, const int64_t* actions, int n, const float* dlogp,
                        const float* dentropy, const float* saved4, void* dlogits, int64_t ldg, void* stream);
 
+/* PPO clipped-surrogate loss of one minibatch and its gradients in closed form (keisei/core/ppo_agent.py:332-372;
+ * value clipping off): out6 = {loss, policy loss, value loss, entropy loss (= -mean entropy), mean(old_logp -
+ * new_logp), clip fraction}; d_* = d loss / d input, multiplied by grad_scale.  All fp32 [n]. */
+int kz_ppo_loss(const float* new_logp, const float* entropy, const float* new_value, const float* old_logp,
+                const float* advantages, const float* returns, int n, float clip_epsilon, float value_coef,
+                float entropy_coef, float grad_scale, float* out6, float* d_logp, float* d_entropy, float* d_value,
+                void* stream);
+
 /* ---- observation input layer of the default policy/value network (keisei/core/neural_network.py:14-28:
  * nn.Conv2d(46, 16, kernel_size=3, padding=1) [+ ReLU], run under bf16 autocast by ppo_agent.py:323) ----
  * kz_obs_conv_fwd: out[n][16][9][9] (bf16) = [relu](conv3x3(obs fp32 [n][46][9][9], weight fp32 [16][46][3][3]) + bias),

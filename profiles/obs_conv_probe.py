@@ -23,10 +23,10 @@ dy = torch.randn(n, 16, 9, 9, device=dev).bfloat16()
 ctas = L.kz_obs_conv_wgrad_ctas(n)
 ws = torch.empty(ctas * 16 * 432, device=dev); dw = torch.empty(16, 46, 3, 3, device=dev); db = torch.empty(16, device=dev)
 wd, bd = w.detach(), b.detach()
-ms = timed(lambda: L.kz_obs_conv_fwd(obs.data_ptr(), wd.data_ptr(), bd.data_ptr(), 16, n, 1, y.data_ptr(), st))
+ms = timed(lambda: L.kz_obs_conv_fwd(obs.data_ptr(), None, wd.data_ptr(), bd.data_ptr(), 16, n, 1, y.data_ptr(), st))
 by = n * (46 * 81 * 4 + 16 * 81 * 2)
 print(f"kz_obs_conv_fwd: {ms*1e3:.1f} us / {n} boards, {by/ms/1e6:.0f} GB/s = {by/ms/1e6/peak:.2f} of measured HBM peak")
-ms = timed(lambda: L.kz_obs_conv_wgrad(obs.data_ptr(), y.data_ptr(), dy.data_ptr(), 1, 16, n, ws.data_ptr(), ctas,
+ms = timed(lambda: L.kz_obs_conv_wgrad(obs.data_ptr(), None, y.data_ptr(), dy.data_ptr(), 1, 16, n, ws.data_ptr(), ctas,
                                        dw.data_ptr(), db.data_ptr(), st))
 by = n * (46 * 81 * 4 + 2 * 16 * 81 * 2)
 print(f"kz_obs_conv_wgrad (+reduce): {ms*1e3:.1f} us, {by/ms/1e6:.0f} GB/s = {by/ms/1e6/peak:.2f}")

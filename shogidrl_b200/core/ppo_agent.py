@@ -16,6 +16,8 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+from .. import rl
+
 from ..utils.policy_mapper import PolicyOutputMapper
 
 
@@ -201,19 +203,25 @@ class PPOAgent:
                                                                                mask_rows=mb)
         new_v = new_v.float()
         old_lp, adv, ret = S["oldlp"][mb], S["adv"][mb], S["ret"][mb]
-        ratio = torch.exp(new_lp - old_lp)
-        policy_loss = -torch.min(ratio * adv, torch.clamp(ratio, 1 - self.clip_epsilon, 1 + self.clip_epsilon) * adv).mean()
-        if self.enable_value_clipping:
-            old_v = S["oldv"][mb]
-            clipped = old_v + torch.clamp(new_v - old_v, -self.clip_epsilon, self.clip_epsilon)
-            value_loss = torch.max(F.mse_loss(new_v.squeeze(), ret.squeeze()), F.mse_loss(clipped.squeeze(), ret.squeeze()))
-        else:
-            value_loss = F.mse_loss(new_v.squeeze(), ret.squeeze())
-        entropy_loss = -entropy.mean()
-        loss = policy_loss + self.value_loss_coeff * value_loss + self.entropy_coef * entropy_loss
         grad_world = getattr(self, "_grad_world", 1)
-        if grad_world > 1:
-            loss = loss / grad_world  # the all-reduce below sums: mean gradient over ranks
+        fused_loss = self.device.type == "cuda" and not self.enable_value_clipping
+        if fused_loss:
+            # clipped surrogate, value and entropy terms, their gradients and the five metrics in one launch
+            loss, stats = rl.ppo_loss(new_lp, entropy, new_v.squeeze(-1) if new_v.dim() > 1 else new_v, old_lp, adv, ret,
+                                      self.clip_epsilon, self.value_loss_coeff, self.entropy_coef, 1.0 / grad_world)
+        else:
+            ratio = torch.exp(new_lp - old_lp)
+            policy_loss = -torch.min(ratio * adv, torch.clamp(ratio, 1 - self.clip_epsilon, 1 + self.clip_epsilon) * adv).mean()
+            if self.enable_value_clipping:
+                old_v = S["oldv"][mb]
+                clipped = old_v + torch.clamp(new_v - old_v, -self.clip_epsilon, self.clip_epsilon)
+                value_loss = torch.max(F.mse_loss(new_v.squeeze(), ret.squeeze()), F.mse_loss(clipped.squeeze(), ret.squeeze()))
+            else:
+                value_loss = F.mse_loss(new_v.squeeze(), ret.squeeze())
+            entropy_loss = -entropy.mean()
+            loss = policy_loss + self.value_loss_coeff * value_loss + self.entropy_coef * entropy_loss
+            if grad_world > 1:
+                loss = loss / grad_world  # the all-reduce below sums: mean gradient over ranks
         self.optimizer.zero_grad(set_to_none=True)
         loss.backward()  # under DistributedDataParallel the gradient all-reduce (NCCL) fires here
         if grad_world > 1:
@@ -222,8 +230,11 @@ class PPOAgent:
         gn = torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.gradient_clip_max_norm)
         self.optimizer.step()
         with torch.no_grad():
-            self._sums += torch.stack([policy_loss, value_loss, entropy_loss, (old_lp - new_lp).mean(),
-                                       ((ratio - 1.0).abs() > self.clip_epsilon).float().mean()]).detach()
+            if fused_loss:
+                self._sums += stats[1:]
+            else:
+                self._sums += torch.stack([policy_loss, value_loss, entropy_loss, (old_lp - new_lp).mean(),
+                                           ((ratio - 1.0).abs() > self.clip_epsilon).float().mean()]).detach()
             self._gn.copy_(gn)
 
     def _static_batch(self, S: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:

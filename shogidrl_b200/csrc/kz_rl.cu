@@ -412,7 +412,71 @@ __global__ void __launch_bounds__(256, 4) kz_eval_bwd_kernel(const void* logits,
   });
 }
 
+// ------------------------------------------------------------------------------------------------
+// PPO clipped-surrogate loss of one minibatch (keisei/core/ppo_agent.py:332-372) with its gradients in closed
+// form: ratio = exp(new_lp - old_lp); policy = -mean(min(ratio A, clamp(ratio, 1 - e, 1 + e) A));
+// value = mean((v - R)^2); entropy term = -mean(H); loss = policy + c_v value + c_e entropy term.
+// One CTA (a minibatch is a few thousand scalars per vector): replaces ~40 elementwise launches and their
+// autograd nodes.  out[0] = loss, out[1..5] = policy, value, entropy term, mean(old_lp - new_lp), clip fraction.
+// Gradients (already scaled by grad_scale, e.g. 1 / world size): torch.min passes the gradient to the smaller
+// argument and ties (ratio inside the clip range: both arguments equal) recombine to the same value, so
+// d policy / d new_lp = -(1/n) A ratio unless the clipped branch is the strict minimum.
+__global__ void __launch_bounds__(1024) kz_ppo_loss_kernel(const float* __restrict__ new_lp, const float* __restrict__ ent,
+                                                           const float* __restrict__ new_v, const float* __restrict__ old_lp,
+                                                           const float* __restrict__ adv, const float* __restrict__ ret, int n,
+                                                           float clip_eps, float value_coef, float entropy_coef,
+                                                           float grad_scale, float* __restrict__ out,
+                                                           float* __restrict__ d_lp, float* __restrict__ d_ent,
+                                                           float* __restrict__ d_v) {
+  __shared__ float red[5][32];
+  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  const float inv_n = 1.0f / (float)n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float lp = new_lp[i], olp = old_lp[i], a = adv[i];
+    const float ratio = expf(lp - olp);
+    const float clamped = fminf(fmaxf(ratio, 1.0f - clip_eps), 1.0f + clip_eps);
+    const float s1 = ratio * a, s2 = clamped * a;
+    acc[0] -= fminf(s1, s2);
+    const float dv = new_v[i] - ret[i];
+    acc[1] += dv * dv;
+    acc[2] -= ent[i];
+    acc[3] += olp - lp;
+    acc[4] += fabsf(ratio - 1.0f) > clip_eps ? 1.f : 0.f;
+    // d min(s1, s2) / d ratio: a through s1 when s1 <= s2 (ties: half through each, and s2 passes it on inside the
+    // range, where the tie happens); through s2 only inside the clip range, i.e. never when s2 is the strict minimum
+    const float g_ratio = (s1 <= s2) ? a : 0.f;
+    d_lp[i] = -inv_n * g_ratio * ratio * grad_scale;
+    d_ent[i] = -inv_n * entropy_coef * grad_scale;
+    d_v[i] = 2.0f * inv_n * dv * value_coef * grad_scale;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    float v = acc[k];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    if (lane == 0) red[k][warp] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float tot[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      float v = lane < (int)(blockDim.x >> 5) ? red[k][lane] : 0.f;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+      tot[k] = v * inv_n;
+    }
+    if (lane == 0) {
+      out[0] = tot[0] + value_coef * tot[1] + entropy_coef * tot[2];
+#pragma unroll
+      for (int k = 0; k < 5; k++) out[1 + k] = tot[k];
+    }
+  }
+}
+
 }  // namespace
+
 
 extern "C" {
 
@@ -472,6 +536,20 @@ int kz_gae_exact(const float* rewards, const float* values, const uint8_t* dones
   if (!rewards || !values || !dones || !last_value || !adv || !ret || T <= 0 || N <= 0) return KZ_E_ARG;
   kz_gae_columns_kernel<<<(N + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       rewards, values, dones, last_value, T, N, gamma, gamma_lambda, adv, ret);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? KZ_OK : fail(e);
+}
+
+int kz_ppo_loss(const float* new_logp, const float* entropy, const float* new_value, const float* old_logp,
+                const float* advantages, const float* returns, int n, float clip_epsilon, float value_coef,
+                float entropy_coef, float grad_scale, float* out6, float* d_logp, float* d_entropy, float* d_value,
+                void* stream) {
+  if (!new_logp || !entropy || !new_value || !old_logp || !advantages || !returns || !out6 || !d_logp || !d_entropy ||
+      !d_value || n <= 0)
+    return KZ_E_ARG;
+  kz_ppo_loss_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      new_logp, entropy, new_value, old_logp, advantages, returns, n, clip_epsilon, value_coef, entropy_coef, grad_scale, out6,
+      d_logp, d_entropy, d_value);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? KZ_OK : fail(e);
 }

@@ -96,3 +96,38 @@ def evaluate_masked(logits: torch.Tensor, mask: torch.Tensor, actions: torch.Ten
     if mask_rows is not None:
         mask_rows = mask_rows.contiguous().long()
     return _MaskedCategoricalEval.apply(logits, mask, actions, mask_rows)
+
+
+class _PPOLoss(torch.autograd.Function):
+    """Clipped-surrogate loss + metrics + closed-form gradients in one launch (kz_ppo_loss)."""
+
+    @staticmethod
+    def forward(ctx, new_lp, entropy, new_v, old_lp, adv, ret, clip_eps, value_coef, entropy_coef, grad_scale):
+        dev = nv.require_cuda(new_lp.device)
+        n = new_lp.shape[0]
+        args = [t.detach().contiguous().float().reshape(-1) for t in (new_lp, entropy, new_v, old_lp, adv, ret)]
+        assert all(t.shape[0] == n for t in args)
+        out = torch.empty(6, dtype=torch.float32, device=dev)
+        grads = torch.empty((3, n), dtype=torch.float32, device=dev)
+        nv.check(nv.lib().kz_ppo_loss(*[t.data_ptr() for t in args], n, float(clip_eps), float(value_coef),
+                                      float(entropy_coef), float(grad_scale), out.data_ptr(), grads[0].data_ptr(),
+                                      grads[1].data_ptr(), grads[2].data_ptr(), nv.stream_ptr(dev)), "kz_ppo_loss")
+        ctx.save_for_backward(grads)
+        ctx.shapes = (new_lp.shape, entropy.shape, new_v.shape)
+        ctx.mark_non_differentiable(out)
+        return out[0].clone(), out
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_out):
+        (grads,) = ctx.saved_tensors
+        g = grads * g_loss
+        s = ctx.shapes
+        return g[0].reshape(s[0]), g[1].reshape(s[1]), g[2].reshape(s[2]), None, None, None, None, None, None, None
+
+
+def ppo_loss(new_lp: torch.Tensor, entropy: torch.Tensor, new_v: torch.Tensor, old_lp: torch.Tensor, adv: torch.Tensor,
+             ret: torch.Tensor, clip_eps: float, value_coef: float, entropy_coef: float, grad_scale: float = 1.0):
+    """-> (loss, stats6): loss = policy + value_coef * value + entropy_coef * entropy_term as a differentiable
+    scalar (gradients w.r.t. new_lp / entropy / new_v, multiplied by ``grad_scale``); stats6 = [loss, policy loss,
+    value loss, entropy term, mean(old_lp - new_lp), clip fraction] (ppo_agent.py:332-372, value clipping off)."""
+    return _PPOLoss.apply(new_lp, entropy, new_v, old_lp, adv, ret, clip_eps, value_coef, entropy_coef, grad_scale)

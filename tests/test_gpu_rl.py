@@ -315,3 +315,34 @@ def test_fused_minibatch_forward_matches_unfused_path():
     for k in g1:
         scale = float(g2[k].abs().max())
         assert float((g1[k] - g2[k]).abs().max()) <= 3e-2 * scale + 1e-6, (k, float((g1[k] - g2[k]).abs().max()), scale)
+
+
+@pytest.mark.parametrize("n", [7, 1024, 16384])
+def test_fused_ppo_loss_matches_torch(n):
+    """kz_ppo_loss against the reference formulas (ppo_agent.py:332-372) written in torch: loss, the five
+    metrics and the gradients w.r.t. new log-probs / entropy / values, with ratios on both sides of the clip range."""
+    from shogidrl_b200 import rl
+    g = torch.Generator(device="cpu").manual_seed(n)
+    old_lp = (-torch.rand(n, generator=g) * 5).cuda()
+    new_lp = (old_lp.cpu() + torch.randn(n, generator=g) * 0.3).cuda().requires_grad_()
+    ent = (torch.rand(n, generator=g) * 4).cuda().requires_grad_()
+    new_v = torch.randn(n, generator=g).cuda().requires_grad_()
+    adv, ret = torch.randn(n, generator=g).cuda(), torch.randn(n, generator=g).cuda()
+    adv[::5] = 0.0
+    eps, cv, ce, scale = 0.2, 0.5, 0.01, 0.5
+    loss, stats = rl.ppo_loss(new_lp, ent, new_v, old_lp, adv, ret, eps, cv, ce, scale)
+    loss.backward()
+    got = [t.grad.clone() for t in (new_lp, ent, new_v)]
+    for t in (new_lp, ent, new_v):
+        t.grad = None
+    ratio = torch.exp(new_lp - old_lp)
+    pol = -torch.min(ratio * adv, torch.clamp(ratio, 1 - eps, 1 + eps) * adv).mean()
+    val = torch.nn.functional.mse_loss(new_v, ret)
+    el = -ent.mean()
+    ref = pol + cv * val + ce * el
+    (ref * scale).backward()
+    assert torch.allclose(loss, ref, rtol=1e-5, atol=1e-6)
+    want = torch.stack([ref, pol, val, el, (old_lp - new_lp).mean(), ((ratio - 1).abs() > eps).float().mean()]).detach()
+    assert torch.allclose(stats, want, rtol=1e-5, atol=1e-6), (stats, want)
+    for a, t in zip(got, (new_lp, ent, new_v)):
+        assert torch.allclose(a, t.grad, rtol=1e-5, atol=1e-9), float((a - t.grad).abs().max())
