@@ -303,3 +303,40 @@ def test_graphed_ppo_update_matches_eager():
     for x, y in zip(pa, pb):
         assert torch.allclose(x, y, rtol=1e-3, atol=1e-4), float((x - y).abs().max())
     assert abs(gna - gnb) <= 1e-3 * max(1.0, gnb)
+
+
+def test_host_pipelined_env_equals_one_batch():
+    """HostPipelinedEnv (2 and 4 groups, host actions, own streams) plays exactly the games a single VecShogiEnv
+    plays with the same seed: group g's games carry the RNG streams of envs [g n/G, (g+1) n/G)."""
+    from shogidrl_b200.host_env import HostPipelinedEnv
+    from shogidrl_b200.vec_env import VecShogiEnv
+    dev = torch.device("cuda:0")
+    n, T = 512, 60
+    ref = VecShogiEnv(n, max_moves_per_game=40, device=dev, seed=77, auto_reset=True)
+    ref.refresh(random_actions=True)
+    acts = [ref.next_actions.clone(), torch.empty_like(ref.next_actions)]
+    rewards = []
+    for t in range(T):
+        out = ref.step(acts[t & 1], random_actions=True, next_out=acts[(t + 1) & 1])
+        rewards.append(out["reward"].clone())
+    rb, rh, rm = [x.cpu() for x in ref.export()]
+    for G in (2, 4):
+        pipe = HostPipelinedEnv(n, groups=G, max_moves_per_game=40, device=dev, seed=77, auto_reset=True)
+        pipe.prime(random_actions=True)
+        got = [[] for _ in range(G)]
+        for t in range(T):
+            for g in range(G):
+                nxt, rew, done, reason, winner = pipe.wait(g)
+                if t > 0:
+                    got[g].append(rew.clone())
+                pipe.h_actions[g].copy_(nxt)          # the host "policy": play the pre-selected legal action
+                pipe.submit(g, random_actions=True)
+        for g in range(G):
+            got[g].append(pipe.wait(g)[1].clone())
+        pipe.synchronize()
+        b = torch.cat([e.export()[0].cpu() for e in pipe.envs]); h = torch.cat([e.export()[1].cpu() for e in pipe.envs])
+        m = torch.cat([e.export()[2].cpu() for e in pipe.envs])
+        assert torch.equal(b, rb) and torch.equal(h, rh) and torch.equal(m[:, :5], rm[:, :5])
+        for t in range(T):
+            assert torch.equal(torch.cat([got[g][t] for g in range(G)]), rewards[t].cpu())
+        assert all(int(e.errors().abs().sum()) == 0 for e in pipe.envs)
