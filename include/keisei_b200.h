@@ -59,8 +59,9 @@ int kz_init_tables(void* stream);
 /* Device game state is one caller-allocated blob (torch.empty(total, dtype=uint8)), SoA by
  * field group: boards [n][96] u8, meta [n][32] u8, repetition tables [n][slots] of 16-byte
  * slots (124-bit Zobrist-style position key + 4-bit occurrence count, open addressing, slots =
- * power of two >= 2*hist_cap) replacing the tuple history of shogi_game.py:347-372.
- * offsets3 (HOST) receives the byte offsets of the three sections. */
+ * power of two >= 2*hist_cap) replacing the tuple history of shogi_game.py:347-372, and a
+ * trailing 256-byte scheduling word block (work counter of the launch in flight).
+ * offsets3 (HOST) receives the byte offsets of the first three sections. */
 int kz_state_layout(int n, int hist_cap, int64_t* offsets3, int64_t* total_bytes);
 
 /* ShogiGame.reset (shogi_game.py:79-130) for the envs whose env_mask byte is non-zero (all

@@ -1,5 +1,5 @@
 #!/bin/bash
-for f in build/v12/*.so; do
+for f in ${VARIANTS:-build/*/*.so}; do
   echo "== $f"
   KZ_LIB_PATH=$PWD/$f python bench.py --steps 48 --warmup 8 --no-cpu-baseline 2>&1 | python -c "
 import sys,json

@@ -538,6 +538,7 @@ struct StepParams {
   int auto_reset;
   int mode;  // 0 = refresh, 1 = step
   int eval_term;
+  int* tile_counter;  // zeroed per launch: tiles (8 games, one per warp) beyond the first are claimed dynamically
 };
 
 __device__ __forceinline__ uint32_t rand32(unsigned long long seed, unsigned long long env, unsigned long long step) {
@@ -575,23 +576,40 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
     return P.actions_i64 ? reinterpret_cast<const long long*>(P.actions)[g]
                          : (long long)reinterpret_cast<const int*>(P.actions)[g];
   };
-  const int g_first = blockIdx.x * WARPS_PER_CTA + warp, g_stride = gridDim.x * WARPS_PER_CTA;
-  uint32_t next_word = fetch_state(g_first);
-  long long next_action = fetch_action(g_first);
+  // When every warp of the CTA runs the same number of games (n a multiple of the CTA's warp count), the CTA works
+  // in lockstep on "tiles" of 8 games: (1) the warps are re-aligned once per game -- warps that run the same code
+  // at the same time share instruction-cache lines (the kernel is close to the GPC instruction-fetch limit;
+  // measured 0.387 -> 0.375 ms; barriers at more points cost more in waiting than they save); (2) tiles after the
+  // first are claimed from a global counter instead of a fixed stride, so CTAs that drew cheap positions take more
+  // tiles and the grid drains together (a static split leaves 200 of 444 CTAs one game longer than the rest, and
+  // the kernel as slow as its unluckiest CTA).  Thread 0 claims two tiles ahead: the id for game i + 1 is needed
+  // at the top of game i for the prefetch, so it is fetched during game i - 1 and handed over through s_tile.
+  const bool lockstep = (P.n % WARPS_PER_CTA) == 0 && P.tile_counter != nullptr;
+  const int ntiles = P.n / WARPS_PER_CTA;
+  __shared__ int s_tile[2];
+  int tile = blockIdx.x, claimed = 0;
+  if (lockstep && threadIdx.x == 0) s_tile[1] = gridDim.x + atomicAdd(P.tile_counter, 1);
+  const int g_stride = gridDim.x * WARPS_PER_CTA;
+  int g = blockIdx.x * WARPS_PER_CTA + warp;
+  uint32_t next_word = fetch_state(g);
+  long long next_action = fetch_action(g);
+  __syncthreads();
 
-  // When every warp of the CTA runs the same number of games, re-align the warps once per game: warps that run
-  // the same code at the same time share instruction-cache lines (the kernel is close to the GPC instruction-fetch
-  // limit; measured 0.387 -> 0.375 ms; barriers at more points cost more in waiting than they save).
-  const bool lockstep = (P.n % WARPS_PER_CTA) == 0;
-  for (int g = g_first; g < P.n; g += g_stride) {
-    if (lockstep) __syncthreads();
+  for (int it = 0; lockstep ? tile < ntiles : g < P.n; it++) {
+    int g_next = g + g_stride;
+    if (lockstep) {
+      __syncthreads();
+      tile = s_tile[(it + 1) & 1];  // the tile after this one
+      g_next = tile * WARPS_PER_CTA + warp;
+      if (threadIdx.x == 0) claimed = gridDim.x + atomicAdd(P.tile_counter, 1);  // two ahead; stored at the loop end
+    }
     // ---- state of this game (prefetched), start fetching the next one
     __syncwarp();
     if (lane < 24) reinterpret_cast<uint32_t*>(ws.board)[lane] = next_word;
     else reinterpret_cast<uint32_t*>(ws.meta)[lane - 24] = next_word;
     const long long a = next_action;
-    next_word = fetch_state(g + g_stride);
-    next_action = fetch_action(g + g_stride);
+    next_word = fetch_state(g_next);
+    next_action = fetch_action(g_next);
     __syncwarp();
     int side = ws.meta[14];
     int status = ws.meta[15];
@@ -994,6 +1012,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
       else mdst[lane - 24] = reinterpret_cast<uint32_t*>(ws.meta)[lane - 24];
     }
     __syncwarp();
+    if (lockstep && threadIdx.x == 0) s_tile[it & 1] = claimed;  // read after the next barrier as tile it + 2
+    g = g_next;
   }
 }
 
@@ -1117,9 +1137,10 @@ namespace {
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return cuda_fail(_e); } while (0)
 
 int g_sm_count = 0;
+
 bool g_host_ready = false;
 
-struct Layout { int64_t off_boards, off_meta, off_hist, total; int rep_slots; };
+struct Layout { int64_t off_boards, off_meta, off_hist, off_sched, total; int rep_slots; };
 Layout layout(int n, int hist_cap) {
   Layout L;
   L.rep_slots = 64;  // power of two >= 2 * hist_cap keeps the load factor below 1/2
@@ -1128,7 +1149,8 @@ Layout layout(int n, int hist_cap) {
   L.off_meta = (int64_t)n * 96;
   L.off_hist = L.off_meta + (int64_t)n * 32;
   L.off_hist = (L.off_hist + 255) & ~(int64_t)255;
-  L.total = L.off_hist + (int64_t)n * L.rep_slots * 16;
+  L.off_sched = L.off_hist + (int64_t)n * L.rep_slots * 16;  // 256 B: the tile counter of the launch in flight
+  L.total = L.off_sched + 256;
   return L;
 }
 
@@ -1157,6 +1179,14 @@ int launch_step(void* state, int n, int hist_cap, StepParams P, cudaStream_t st)
   int grid = g_sm_count * CTAS_PER_SM;
   if (grid > ctas_needed) grid = ctas_needed;
   const size_t dyn = sizeof(WarpScratch) * WARPS_PER_CTA;
+  P.tile_counter = nullptr;
+#ifndef KZ_STATIC_TILES
+  if (grid < ctas_needed && n % WARPS_PER_CTA == 0) {
+    // launches on one state buffer are ordered by their data dependence, so the counter can live in it
+    P.tile_counter = reinterpret_cast<int*>(base + L.off_sched);
+    CK(cudaMemsetAsync(P.tile_counter, 0, sizeof(int), st));
+  }
+#endif
   if (P.mode == 1) kz_step_kernel<1><<<grid, WARPS_PER_CTA * 32, dyn, st>>>(P);
   else kz_step_kernel<0><<<grid, WARPS_PER_CTA * 32, dyn, st>>>(P);
   CK(cudaGetLastError());
