@@ -161,6 +161,106 @@ def run_reference(args):
     return 0
 
 
+def run_reference_ppo(args):
+    """--impl reference --workload ppo: the reference's sequential CPU trainer restated -- one game, batch-1
+    select_action (masked softmax + Categorical sample, ppo_agent.py:134-223), ExperienceBuffer GAE
+    (experience_buffer.py:99-145), then PPOAgent.learn (ppo_agent.py:243-460: ppo_epochs x minibatches of 64, clipped
+    surrogate + value MSE + entropy, clip_grad_norm_ 0.5, Adam) -- on the oracle engine and the default CNN
+    (neural_network.py:10-29) in plain fp32 PyTorch on all host threads.  One step = one epoch of `--ref-ppo-steps`
+    timesteps (a bounded sample of the reference's steps_per_epoch = 2048); value = timesteps per second."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+    import torch
+    import torch.nn as nn
+    from oracle import oracle as orc
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(SEED)
+    S, MB, EPOCHS = args.ref_ppo_steps, 64, args.ppo_epochs
+    gamma, lam, clip_eps, cv, ce = 0.99, 0.95, 0.2, 0.5, 0.01
+
+    class Net(nn.Module):  # keisei/core/neural_network.py:10-29
+        def __init__(self):
+            super().__init__()
+            self.conv = nn.Conv2d(46, 16, 3, padding=1)
+            self.policy_head = nn.Linear(16 * 81, 13527)
+            self.value_head = nn.Linear(16 * 81, 1)
+
+        def forward(self, x):
+            h = torch.relu(self.conv(x)).flatten(1)
+            return self.policy_head(h), self.value_head(h).squeeze(-1)
+
+    def dist_of(logits, mask):
+        probs = torch.softmax(torch.where(mask, logits, torch.full((), float("-inf"))), dim=-1)
+        return torch.distributions.Categorical(probs=probs)
+
+    model = Net()
+    opt = torch.optim.Adam(model.parameters(), lr=3e-4)
+    game = orc.OracleGame(MAX_MOVES)
+    shuffle_rng = np.random.default_rng(SEED)
+    steps = max(1, min(args.steps, 8))
+    warm = min(args.warmup, 1)
+
+    def epoch():
+        obs = np.zeros((S, 46, 9, 9), np.float32); masks = np.zeros((S, 13527), np.uint8)
+        act = np.zeros(S, np.int64); lp = np.zeros(S, np.float32); val = np.zeros(S, np.float32)
+        rew = np.zeros(S, np.float32); done = np.zeros(S, np.uint8)
+        t_roll = time.perf_counter()
+        for t in range(S):
+            obs[t] = game.observation(); masks[t] = game.legal_mask()
+            with torch.no_grad():
+                logits, v = model(torch.from_numpy(obs[t:t + 1]))
+                d = dist_of(logits, torch.from_numpy(masks[t:t + 1]).bool())
+                a = d.sample()
+                lp[t] = float(d.log_prob(a)); val[t] = float(v); act[t] = int(a)
+            r, dn, _, _ = game.make_move(int(a))
+            rew[t], done[t] = r, dn
+            if dn:
+                game.reset()
+        with torch.no_grad():
+            last_v = float(model(torch.from_numpy(game.observation()[None]))[1])
+        adv, ret = orc.gae(rew[:, None], val[:, None], done[:, None], np.float32(last_v), gamma, lam)
+        t_roll = time.perf_counter() - t_roll
+        to = torch.from_numpy
+        obs_t, mask_t, act_t = to(obs), to(masks).bool(), to(act)
+        lp_t, adv_t, ret_t = to(lp), to(adv[:, 0].copy()), to(ret[:, 0].copy())
+        adv_t = (adv_t - adv_t.mean()) / (adv_t.std() + 1e-8)
+        for _ in range(EPOCHS):
+            idx = shuffle_rng.permutation(S)  # ppo_agent.py:298
+            for s0 in range(0, S, MB):
+                mb = torch.from_numpy(idx[s0:s0 + MB])
+                logits, v = model(obs_t[mb])
+                d = dist_of(logits, mask_t[mb])
+                new_lp, ent = d.log_prob(act_t[mb]), d.entropy()
+                ratio = torch.exp(new_lp - lp_t[mb])
+                pol = -torch.min(ratio * adv_t[mb], torch.clamp(ratio, 1 - clip_eps, 1 + clip_eps) * adv_t[mb]).mean()
+                loss = pol + cv * torch.nn.functional.mse_loss(v, ret_t[mb]) - ce * ent.mean()
+                opt.zero_grad()
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_(model.parameters(), 0.5)
+                opt.step()
+        return t_roll
+
+    for _ in range(warm):
+        epoch()
+    t0 = time.perf_counter()
+    roll = sum(epoch() for _ in range(steps))
+    dt = time.perf_counter() - t0
+    value = S * steps / dt
+    sample = (f"{steps} epochs x {S} timesteps of one game (reference default: 2048), minibatch {MB}, ppo_epochs {EPOCHS}, "
+              f"C oracle engine + fp32 PyTorch CPU model on {threads} threads (the pure-Python reference cannot run on the GPU box)")
+    emit({"impl": "reference", "metric": "PPO self-play samples/sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+          "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "config": {"workload": "BASELINE config 3 on the host: PPO self-play, cnn policy-value net, sequential trainer; " + sample,
+                     "rollout_samples_per_s": S * steps / roll, "update_samples_per_s": S * steps / max(1e-9, dt - roll)},
+          "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+          "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+    return 0
+
+
 def run_product(args):
     import torch
     import torch.distributed as dist
@@ -256,6 +356,33 @@ def run_product(args):
     barrier()
     serial_ms = 1e3 * (time.perf_counter() - t0)
 
+    # (c) every output on the host: as (a), plus the step's 46x9x9 observations and 13,527-byte legal masks copied to
+    #     pinned host memory -- what a caller that keeps the policy tower off the GPU would pay (PCIe-bound).
+    h_obs = torch.empty((n, 46, 9, 9), dtype=torch.float32).pin_memory()
+    h_mask = torch.empty((n, MASK_PAD_STRIDE), dtype=torch.uint8).pin_memory()
+    full_steps = 4
+
+    def full_step(i):
+        a = act[i & 1]
+        a.copy_(h_act, non_blocking=True)
+        env.step(a, obs=obs_buf[i % SLOTS], mask=mask_buf[i % SLOTS][:, :13527], random_actions=True,
+                 next_out=env.next_actions)
+        h_res.copy_(env.results, non_blocking=True)
+        h_obs.copy_(obs_buf[i % SLOTS], non_blocking=True)
+        h_mask.copy_(mask_buf[i % SLOTS], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        h_act.copy_(h_res[: 8 * n].view(torch.int64))
+
+    full_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(full_steps):
+        full_step(i)
+    barrier()
+    full_ms = 1e3 * (time.perf_counter() - t0)
+    full_d2h = 15 * n + h_obs.numel() * 4 + h_mask.numel()
+    del h_obs, h_mask
+
     from shogidrl_b200.host_env import HostPipelinedEnv
     G = 2
     del env
@@ -285,9 +412,9 @@ def run_product(args):
     errs += sum(int((e.errors() != 0).sum()) for e in pipe.envs)
 
     if world > 1:
-        t = torch.tensor([ms_total, e2e_ms, kernel_ms, serial_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_total, e2e_ms, kernel_ms, serial_ms, full_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_ms, kernel_ms, serial_ms = [float(x) for x in t]
+        ms_total, e2e_ms, kernel_ms, serial_ms, full_ms = [float(x) for x in t]
         e = torch.tensor([errs], device=dev)
         dist.all_reduce(e)
         errs = int(e)
@@ -323,10 +450,15 @@ def run_product(args):
             "e2e": {"value": world * n * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * n,
                     "d2h_bytes_per_step": 15 * n, "steps": e2e_steps,
                     "serial_value": world * n * e2e_steps / (serial_ms * 1e-3),
+                    "all_outputs_to_host_value": world * n * full_steps / (full_ms * 1e-3),
+                    "all_outputs_d2h_bytes_per_step": full_d2h,
                     "note": "HostPipelinedEnv (2 groups, 2 streams): actions from pinned host memory, reward/done/reason/winner/"
                             "next-action read back to pinned host memory every step, host waits for each group's results before "
                             "submitting its next actions; obs/mask stay in HBM for the policy tower; serial_value = the same "
-                            "through one VecShogiEnv with copy -> kernel -> copy -> synchronise in sequence"},
+                            "through one VecShogiEnv with copy -> kernel -> copy -> synchronise in sequence; all_outputs_to_host_value = the "
+                            "serial path when the observations and legal masks are ALSO copied to pinned host memory every "
+                            "step (1.86 GB per 65,536 games: PCIe-bound; only a caller with its policy network off the GPU "
+                            "needs that)"},
             "gpu_launches": args.steps,
             "clocks": clocks,
         }
@@ -457,10 +589,11 @@ def main():
     ap.add_argument("--ppo-epochs", type=int, default=10)
     ap.add_argument("--ppo-minibatch", type=int, default=16384)
     ap.add_argument("--ppo-model", default="cnn", choices=["cnn", "resnet"])
+    ap.add_argument("--ref-ppo-steps", type=int, default=512, help="timesteps per epoch of the CPU PPO reference arm")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference_ppo(args) if args.workload == "ppo" else run_reference(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun when called directly with --gpus N

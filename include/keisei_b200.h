@@ -166,6 +166,14 @@ int kz_eval_masked_fwd(const void* logits, int logits_bf16, int64_t ld, const ui
 int kz_eval_masked_bwd(const void* logits, int logits_bf16, int64_t ld, const uint8_t* mask, int64_t ldm,
                        const int64_t* mask_rows, const int64_t* actions, int n, const float* dlogp,
                        const float* dentropy, const float* saved4, void* dlogits, int64_t ldg, void* stream);
+/* The same backward that also accumulates the column sums of dlogits -- the gradient of the policy head's bias
+ * (nn.Linear(…, 13527), keisei/core/neural_network.py:20) -- into dbias fp32 [>= 13527], which the caller has zeroed:
+ * dlogits is non-zero only at legal actions (~0.5 % of a row), so the bias gradient is a sparse scatter-add (fp32
+ * reductions in L2, taken before the rounding to the dlogits dtype) instead of a second pass over [n][13536]. */
+int kz_eval_masked_bwd_bias(const void* logits, int logits_bf16, int64_t ld, const uint8_t* mask, int64_t ldm,
+                            const int64_t* mask_rows, const int64_t* actions, int n, const float* dlogp,
+                            const float* dentropy, const float* saved4, void* dlogits, int64_t ldg, float* dbias,
+                            void* stream);
 
 /* PPO clipped-surrogate loss of one minibatch and its gradients in closed form (keisei/core/ppo_agent.py:332-372;
  * value clipping off): out6 = {loss, policy loss, value loss, entropy loss (= -mean entropy), mean(old_logp -
@@ -189,6 +197,21 @@ int kz_obs_conv_fwd(const float* obs, const int64_t* obs_rows, const float* weig
 int kz_obs_conv_wgrad_ctas(int n);
 int kz_obs_conv_wgrad(const float* obs, const int64_t* obs_rows, const void* y_bf16, const void* dout, int dout_bf16,
                       int cout, int n, float* workspace, int ctas, float* dweight, float* dbias, void* stream);
+
+/* ---- tail of a PPO minibatch update: torch.nn.utils.clip_grad_norm_(parameters, max_norm) followed by
+ * torch.optim.Adam.step() (keisei/core/ppo_agent.py:405-413, optimizer built at :66-80), fused: one read of every
+ * gradient for the global L2 norm, then one pass that applies the clip coefficient min(1, max_norm / (norm + 1e-6)),
+ * optional L2 weight decay (g += wd * p) and the Adam update with bias correction on fp32 tensors, in place.
+ *   params / grads / exp_avg / exp_avg_sq / steps: HOST arrays of `count` DEVICE pointers (fp32 tensors of numel[i]
+ *   elements; steps[i] = that parameter's step counter as a device fp32 scalar, ALREADY incremented for this step,
+ *   which is where torch's capturable Adam keeps it).  workspace: device fp32 [>= kz_adam_clip_workspace(count, numel)].
+ *   norm_out2 (device fp32 [2]) receives {total gradient norm before clipping, clip coefficient}.
+ * Deterministic; the gradients themselves are left unscaled. */
+long long kz_adam_clip_workspace(int count, const int64_t* numel);
+int kz_adam_clip_step(int count, void* const* params, const void* const* grads, void* const* exp_avg,
+                      void* const* exp_avg_sq, const void* const* steps, const int64_t* numel, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, float max_norm, float* workspace,
+                      int64_t workspace_floats, float* norm_out2, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkeisei_b200.so")
-SOURCES = ["kz_engine.cu", "kz_rl.cu", "kz_nn.cu"]
+SOURCES = ["kz_engine.cu", "kz_rl.cu", "kz_nn.cu", "kz_opt.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 

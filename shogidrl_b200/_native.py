@@ -22,7 +22,7 @@ EXPORTS = [
     "kz_abi_version", "kz_last_cuda_error", "kz_init_tables", "kz_state_layout", "kz_reset", "kz_load_positions",
     "kz_export_positions", "kz_piece_targets", "kz_refresh", "kz_step", "kz_legal_mask", "kz_observe", "kz_errors", "kz_sample_masked",
     "kz_gae", "kz_gae_exact", "kz_eval_masked_fwd", "kz_eval_masked_bwd", "kz_obs_conv_fwd", "kz_obs_conv_wgrad_ctas",
-    "kz_obs_conv_wgrad", "kz_ppo_loss",
+    "kz_obs_conv_wgrad", "kz_ppo_loss", "kz_eval_masked_bwd_bias", "kz_adam_clip_workspace", "kz_adam_clip_step",
 ]
 
 
@@ -63,6 +63,9 @@ def lib() -> C.CDLL:
     L.kz_gae_exact.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp, vp]
     L.kz_eval_masked_fwd.argtypes = [vp, i32, i64, vp, i64, vp, vp, i32, vp, vp, vp, vp]
     L.kz_eval_masked_bwd.argtypes = [vp, i32, i64, vp, i64, vp, vp, i32, vp, vp, vp, vp, i64, vp]
+    L.kz_eval_masked_bwd_bias.argtypes = [vp, i32, i64, vp, i64, vp, vp, i32, vp, vp, vp, vp, i64, vp, vp]
+    L.kz_adam_clip_workspace.argtypes = [i32, vp]
+    L.kz_adam_clip_step.argtypes = [i32, vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, f32, vp, i64, vp, vp]
     L.kz_obs_conv_fwd.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp]
     L.kz_ppo_loss.argtypes = [vp, vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, vp, vp, vp, vp, vp]
     L.kz_obs_conv_wgrad_ctas.argtypes = [i32]
@@ -70,7 +73,7 @@ def lib() -> C.CDLL:
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("kz_last_cuda_error",):
-            fn.restype = i32
+            fn.restype = i64 if name == "kz_adam_clip_workspace" else i32
     _lib = L
     return L
 

@@ -159,6 +159,9 @@ class PPOAgent:
         self._sums = torch.zeros(5, device=d) if getattr(self, "_sums", None) is None else self._sums.zero_()
         if getattr(self, "_gn", None) is None:
             self._gn = torch.zeros((), device=d)
+            self._gn2 = torch.zeros(2, device=d)  # {gradient norm, clip coefficient} of the fused optimizer tail
+        self._fused_optimizer = (d.type == "cuda" and bool(getattr(self.config.training, "fused_optimizer", True))
+                                 and rl.adam_clip_applicable(self.optimizer))
         updates = 0
         in_place = (getattr(getattr(self.model, "module", self.model), "fused_minibatch", False)
                     and not self._is_obs_scaler() and d.type == "cuda")
@@ -227,8 +230,12 @@ class PPOAgent:
         if grad_world > 1:
             from ..training import distributed as kd
             kd.all_reduce_grads(self.model.parameters())
-        gn = torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.gradient_clip_max_norm)
-        self.optimizer.step()
+        if self._fused_optimizer:
+            # global-norm clip + Adam on the optimizer's own state tensors in three launches (csrc/kz_opt.cu)
+            gn = rl.adam_clip_step(self.optimizer, self.gradient_clip_max_norm, self._gn2)
+        else:
+            gn = torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.gradient_clip_max_norm)
+            self.optimizer.step()
         with torch.no_grad():
             if fused_loss:
                 self._sums += stats[1:]

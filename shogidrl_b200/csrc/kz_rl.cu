@@ -379,7 +379,7 @@ __device__ __forceinline__ void zero_row(char* p, size_t bytes, int lane) {
 __global__ void __launch_bounds__(256, 4) kz_eval_bwd_kernel(const void* logits, int bf16, long long ld, const uint8_t* mask,
                                                           long long ldm, const long long* mask_rows, const long long* actions,
                                                           int n, const float* dlogp, const float* dent, const float* saved,
-                                                          void* dlogits, long long ldg) {
+                                                          void* dlogits, long long ldg, float* dbias) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
@@ -409,6 +409,7 @@ __global__ void __launch_bounds__(256, 4) kz_eval_bwd_kernel(const void* logits,
     const float g = ge * p * (ent_g(p, eps) - S) + wl * ((i == a ? 1.f : 0.f) - p);
     if (bf16) reinterpret_cast<__nv_bfloat16*>(grow)[i] = __float2bfloat16(g);
     else reinterpret_cast<float*>(grow)[i] = g;
+    if (dbias) atomicAdd(dbias + i, g);  // column sum = bias gradient of the policy head (result unused: RED in L2)
   });
 }
 
@@ -525,7 +526,21 @@ int kz_eval_masked_bwd(const void* logits, int logits_bf16, int64_t ld, const ui
     return KZ_E_ARG;
   kz_eval_bwd_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       logits, logits_bf16, ld, mask, ldm, reinterpret_cast<const long long*>(mask_rows),
-      reinterpret_cast<const long long*>(actions), n, dlogp, dentropy, saved4, dlogits, ldg);
+      reinterpret_cast<const long long*>(actions), n, dlogp, dentropy, saved4, dlogits, ldg, nullptr);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? KZ_OK : fail(e);
+}
+
+int kz_eval_masked_bwd_bias(const void* logits, int logits_bf16, int64_t ld, const uint8_t* mask, int64_t ldm,
+                            const int64_t* mask_rows, const int64_t* actions, int n, const float* dlogp,
+                            const float* dentropy, const float* saved4, void* dlogits, int64_t ldg, float* dbias,
+                            void* stream) {
+  if (!logits || !mask || !actions || !dlogp || !dentropy || !saved4 || !dlogits || !dbias || n <= 0 ||
+      ld < KZ_NUM_ACTIONS || ldm < KZ_NUM_ACTIONS || ldg < KZ_NUM_ACTIONS)
+    return KZ_E_ARG;
+  kz_eval_bwd_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      logits, logits_bf16, ld, mask, ldm, reinterpret_cast<const long long*>(mask_rows),
+      reinterpret_cast<const long long*>(actions), n, dlogp, dentropy, saved4, dlogits, ldg, dbias);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? KZ_OK : fail(e);
 }

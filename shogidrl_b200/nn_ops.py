@@ -107,13 +107,19 @@ class _PolicyHeadEval(torch.autograd.Function):
         n = hb.shape[0]
         dlogits = torch.empty((n, _LD), dtype=torch.bfloat16, device=dev)
         dlogits[:, nv.NUM_ACTIONS:].zero_()                             # the kernel clears and fills [0, 13527)
-        nv.check(nv.lib().kz_eval_masked_bwd(logits.data_ptr(), 1, _LD, mask.data_ptr(), mask.stride(0), nv.ptr(mask_rows),
-                                             actions.data_ptr(), n, dlogp.contiguous().float().data_ptr(),
-                                             dent.contiguous().float().data_ptr(), saved.data_ptr(), dlogits.data_ptr(), _LD,
-                                             nv.stream_ptr(dev)), "kz_eval_masked_bwd")
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
+        # bias gradient = column sums of dlogits: scatter-added by the same kernel (only legal entries are non-zero)
+        db32 = torch.zeros(_LD, dtype=torch.float32, device=dev) if want_db else None
+        common = (logits.data_ptr(), 1, _LD, mask.data_ptr(), mask.stride(0), nv.ptr(mask_rows), actions.data_ptr(), n,
+                  dlogp.contiguous().float().data_ptr(), dent.contiguous().float().data_ptr(), saved.data_ptr(),
+                  dlogits.data_ptr(), _LD)
+        if want_db:
+            nv.check(nv.lib().kz_eval_masked_bwd_bias(*common, db32.data_ptr(), nv.stream_ptr(dev)), "kz_eval_masked_bwd_bias")
+        else:
+            nv.check(nv.lib().kz_eval_masked_bwd(*common, nv.stream_ptr(dev)), "kz_eval_masked_bwd")
         dh = torch.mm(dlogits, wp).to(ctx.hdtype) if ctx.needs_input_grad[0] else None
         dw = torch.mm(dlogits.t(), hb)[: nv.NUM_ACTIONS].to(ctx.wdtype) if ctx.needs_input_grad[1] else None
-        db = dlogits.sum(0, dtype=torch.float32)[: nv.NUM_ACTIONS].to(ctx.wdtype) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        db = db32[: nv.NUM_ACTIONS].to(ctx.wdtype) if want_db else None
         return dh, dw, db, None, None, None
 
 

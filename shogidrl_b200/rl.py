@@ -1,6 +1,8 @@
-"""Device-side agent/buffer primitives: masked categorical sampling and GAE (C ABI: kz_sample_masked, kz_gae)."""
+"""Device-side agent/buffer primitives: masked categorical sampling, GAE, masked evaluation, the PPO loss and the
+clip + Adam tail of an update (C ABI: kz_sample_masked, kz_gae, kz_eval_masked_*, kz_ppo_loss, kz_adam_clip_step)."""
 from __future__ import annotations
 
+import ctypes as C
 from typing import Optional, Tuple
 
 import torch
@@ -131,3 +133,56 @@ def ppo_loss(new_lp: torch.Tensor, entropy: torch.Tensor, new_v: torch.Tensor, o
     scalar (gradients w.r.t. new_lp / entropy / new_v, multiplied by ``grad_scale``); stats6 = [loss, policy loss,
     value loss, entropy term, mean(old_lp - new_lp), clip fraction] (ppo_agent.py:332-372, value clipping off)."""
     return _PPOLoss.apply(new_lp, entropy, new_v, old_lp, adv, ret, clip_eps, value_coef, entropy_coef, grad_scale)
+
+
+def adam_clip_applicable(optimizer: torch.optim.Optimizer) -> bool:
+    """The fused tail stands in for ``clip_grad_norm_`` + ``optimizer.step()`` exactly when the optimizer is a plain
+    torch.optim.Adam (one parameter group, no amsgrad / maximize, float lr) over dense fp32 CUDA parameters."""
+    if type(optimizer) is not torch.optim.Adam or len(optimizer.param_groups) != 1:
+        return False
+    g = optimizer.param_groups[0]
+    if g.get("amsgrad") or g.get("maximize") or g.get("differentiable") or isinstance(g["lr"], torch.Tensor):
+        return False
+    return all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and not p.is_sparse for p in g["params"])
+
+
+def adam_clip_step(optimizer: torch.optim.Adam, max_norm: float, norm_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``clip_grad_norm_(params, max_norm)`` + ``optimizer.step()`` in three launches (kz_adam_clip_step): returns the
+    total gradient norm before clipping as a device scalar.  Works on the optimizer's own state tensors (``step``,
+    ``exp_avg``, ``exp_avg_sq``, created here the way torch.optim.Adam creates them when capturable), so
+    ``optimizer.state_dict()`` / checkpoints stay what the reference writes (ppo_agent.py:462-487).  No host
+    synchronisation: safe under CUDA-graph capture once the state exists."""
+    group = optimizer.param_groups[0]
+    params = [p for p in group["params"] if p.grad is not None]
+    if not params:
+        return torch.zeros((), device=group["params"][0].device)
+    dev = nv.require_cuda(params[0].device)
+    steps, grads = [], []
+    for p in params:
+        st = optimizer.state[p]
+        if len(st) == 0:
+            st["step"] = torch.zeros((), dtype=torch.float32, device=dev)
+            st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        if not (torch.is_tensor(st["step"]) and st["step"].is_cuda and st["step"].dtype == torch.float32):
+            st["step"] = torch.as_tensor(float(st["step"]), dtype=torch.float32, device=dev)  # loaded non-capturable state
+        steps.append(st["step"])
+        g = p.grad
+        grads.append(g if g.dtype == torch.float32 and g.is_contiguous() else g.float().contiguous())
+    torch._foreach_add_(steps, 1.0)
+    n = len(params)
+    numel = (C.c_int64 * n)(*[p.numel() for p in params])
+    L = nv.lib()
+    need = int(L.kz_adam_clip_workspace(n, numel))
+    ws = torch.empty(max(need, 1), dtype=torch.float32, device=dev)
+    out = norm_out if norm_out is not None else torch.empty(2, dtype=torch.float32, device=dev)
+    assert out.numel() >= 2 and out.dtype == torch.float32 and out.is_contiguous()
+    arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+    b1, b2 = group["betas"]
+    nv.check(L.kz_adam_clip_step(n, arr(params), arr(grads), arr([optimizer.state[p]["exp_avg"] for p in params]),
+                                 arr([optimizer.state[p]["exp_avg_sq"] for p in params]), arr(steps), numel,
+                                 float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                                 float(group["weight_decay"]), float(max_norm), ws.data_ptr(), ws.numel(), out.data_ptr(),
+                                 nv.stream_ptr(dev)), "kz_adam_clip_step")
+    optimizer._opt_called = True  # what LRScheduler.step() looks at before warning about the call order
+    return out[0]

@@ -305,6 +305,59 @@ def test_graphed_ppo_update_matches_eager():
     assert abs(gna - gnb) <= 1e-3 * max(1.0, gnb)
 
 
+@pytest.mark.parametrize("model_kind", ["cnn", "resnet"])
+def test_fused_optimizer_tail_matches_torch_optimizer(model_kind):
+    """PPOAgent.learn with the fused clip + Adam tail (kz_adam_clip_step on the optimizer's own state) against
+    clip_grad_norm_ + torch.optim.Adam.step(): same metrics, gradient norm, parameters and optimizer state, and a
+    save_model / load_model round trip of that state into an agent that uses the stock optimizer."""
+    from shogidrl_b200.core import ActorCritic, ActorCriticResTower, PPOAgent
+    dev = torch.device("cuda:0")
+    B, mbs = 512, 128
+    g = torch.Generator(device="cpu").manual_seed(2)
+    mask = torch.rand(B, 13536, generator=g) < 0.004
+    mask[:, 0] = True
+    mask = mask.to(dev)
+    batch = {"obs": torch.rand(B, 46, 9, 9, generator=g).to(dev), "actions": torch.zeros(B, dtype=torch.int64, device=dev),
+             "log_probs": torch.full((B,), -3.0, device=dev), "values": torch.zeros(B, device=dev),
+             "advantages": torch.randn(B, generator=g).to(dev), "returns": torch.randn(B, generator=g).to(dev),
+             "legal_masks": mask[:, :13527]}
+
+    class Buf:
+        def get_batch(self):
+            return batch
+
+    def run(fused):
+        cfg = make_config(device="cuda", ppo_epochs=2, minibatch_size=mbs, steps_per_epoch=B)
+        cfg.training.fused_optimizer = fused
+        cfg.training.cuda_graph_update = False
+        torch.manual_seed(7)
+        model = ActorCritic(46, 13527) if model_kind == "cnn" else ActorCriticResTower(46, 13527, 2, 32, 0.25)
+        agent = PPOAgent(model, cfg, dev, use_mixed_precision=True)
+        m = agent.learn(Buf())
+        assert agent._fused_optimizer == fused
+        return agent, m
+
+    a, ma = run(True)
+    b, mb_ = run(False)
+    for k in ma:
+        assert abs(ma[k] - mb_[k]) <= 2e-3 * max(1.0, abs(mb_[k])), (k, ma[k], mb_[k])
+    assert abs(a.last_gradient_norm - b.last_gradient_norm) <= 2e-3 * max(1.0, b.last_gradient_norm)
+    for (k, x), y in zip(a.model.named_parameters(), b.model.parameters()):
+        assert torch.allclose(x, y, rtol=2e-3, atol=2e-4), (k, float((x - y).abs().max()))
+        sa, sb = a.optimizer.state[x], b.optimizer.state[y]
+        assert float(sa["step"]) == float(sb["step"]) == 8
+        assert torch.allclose(sa["exp_avg"], sb["exp_avg"], rtol=5e-2, atol=1e-5), k
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "ck.pth")
+        a.save_model(path, global_timestep=123)
+        out = b.load_model(path)
+        assert out["global_timestep"] == 123 and "error" not in out
+        for x, y in zip(a.model.parameters(), b.model.parameters()):
+            assert torch.equal(x, y) and torch.equal(a.optimizer.state[x]["exp_avg_sq"], b.optimizer.state[y]["exp_avg_sq"])
+        assert all(np.isfinite(v) for v in b.learn(Buf()).values())  # the stock optimizer continues from the fused state
+
+
 def test_host_pipelined_env_equals_one_batch():
     """HostPipelinedEnv (2 and 4 groups, host actions, own streams) plays exactly the games a single VecShogiEnv
     plays with the same seed: group g's games carry the RNG streams of envs [g n/G, (g+1) n/G)."""

@@ -346,3 +346,50 @@ def test_fused_ppo_loss_matches_torch(n):
     assert torch.allclose(stats, want, rtol=1e-5, atol=1e-6), (stats, want)
     for a, t in zip(got, (new_lp, ent, new_v)):
         assert torch.allclose(a, t.grad, rtol=1e-5, atol=1e-9), float((a - t.grad).abs().max())
+
+
+@pytest.mark.parametrize("weight_decay,max_norm", [(0.0, 0.5), (0.01, 0.5), (0.0, 1e9)])
+def test_fused_clip_adam_matches_torch(weight_decay, max_norm):
+    """kz_adam_clip_step against torch.nn.utils.clip_grad_norm_ + torch.optim.Adam(capturable) (ppo_agent.py:405-413)
+    over several steps on tensors of ragged sizes (vector body, scalar tails, a 1-element tensor): parameters,
+    both moments, the step counters and the reported gradient norm.  fp32 tolerance 1e-5 relative."""
+    from shogidrl_b200 import rl
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(5)
+    shapes = [(1353, 129), (16, 46, 3, 3), (4096,), (7,), (1,), (3, 4099)]
+    base = [torch.randn(s, generator=g) for s in shapes]
+    pa = [torch.nn.Parameter(b.clone().to(dev)) for b in base]
+    pb = [torch.nn.Parameter(b.clone().to(dev)) for b in base]
+    kw = dict(lr=3e-4, weight_decay=weight_decay, capturable=True)
+    oa, ob = torch.optim.Adam(pa, **kw), torch.optim.Adam(pb, **kw)
+    assert rl.adam_clip_applicable(oa)
+    for it in range(6):
+        grads = [torch.randn(s, generator=g) * (10.0 if it % 2 else 0.01) for s in shapes]  # clipped and unclipped steps
+        for p, q, gr in zip(pa, pb, grads):
+            p.grad = gr.clone().to(dev)
+            q.grad = gr.clone().to(dev)
+        gn_a = rl.adam_clip_step(oa, max_norm)
+        gn_b = torch.nn.utils.clip_grad_norm_(pb, max_norm=max_norm)
+        ob.step()
+        assert torch.allclose(gn_a, gn_b, rtol=1e-5), (float(gn_a), float(gn_b))
+        for p, q in zip(pa, pb):
+            assert torch.allclose(p, q, rtol=1e-5, atol=1e-7), (it, tuple(p.shape), float((p - q).abs().max()))
+            sa, sb = oa.state[p], ob.state[q]
+            assert float(sa["step"]) == float(sb["step"]) == it + 1
+            assert torch.allclose(sa["exp_avg"], sb["exp_avg"], rtol=1e-5, atol=1e-9)
+            assert torch.allclose(sa["exp_avg_sq"], sb["exp_avg_sq"], rtol=1e-5, atol=1e-12)
+    # the state is torch's own: the stock optimizer continues from it, and a state_dict round trip keeps it
+    sd = oa.state_dict()
+    oc = torch.optim.Adam(pa, **kw)
+    oc.load_state_dict(sd)
+    assert float(oc.state[pa[0]]["step"]) == 6 and torch.equal(oc.state[pa[0]]["exp_avg"], oa.state[pa[0]]["exp_avg"])
+
+
+def test_fused_clip_adam_rejects_what_it_cannot_mirror():
+    from shogidrl_b200 import rl
+    p = [torch.nn.Parameter(torch.zeros(8, device="cuda"))]
+    assert rl.adam_clip_applicable(torch.optim.Adam(p, lr=1e-3))
+    assert not rl.adam_clip_applicable(torch.optim.Adam(p, lr=1e-3, amsgrad=True))
+    assert not rl.adam_clip_applicable(torch.optim.AdamW(p, lr=1e-3))
+    assert not rl.adam_clip_applicable(torch.optim.SGD(p, lr=1e-3))
+    assert not rl.adam_clip_applicable(torch.optim.Adam([{"params": p}, {"params": [torch.nn.Parameter(torch.zeros(2, device="cuda"))]}], lr=1e-3))
