@@ -164,7 +164,7 @@ def test_scripted_sennichite(golden_dir):
     assert int(z["senn_reasons"][-1]) == 4 and len(a0) == 13
 
 
-@pytest.mark.parametrize("n,T,max_moves", [(1024, 160, 500), (512, 120, 40)])
+@pytest.mark.parametrize("n,T,max_moves", [(1024, 160, 500), (512, 120, 40), (1001, 48, 30), (3, 64, 20)])  # last two: ragged batches (not a multiple of the 8 games a CTA runs in lockstep)
 def test_selfplay_vs_oracle(n, T, max_moves):
     """Device self-play with the fused uniform-random legal action and auto-reset, against the C oracle
     playing the same counter-based RNG: actions, rewards, dones, reasons, legal counts every step, and
