@@ -206,11 +206,12 @@ int kz_obs_conv_wgrad(const float* obs, const int64_t* obs_rows, const void* y_b
  *   elements; steps[i] = that parameter's step counter as a device fp32 scalar, ALREADY incremented for this step,
  *   which is where torch's capturable Adam keeps it).  workspace: device fp32 [>= kz_adam_clip_workspace(count, numel)].
  *   norm_out2 (device fp32 [2]) receives {total gradient norm before clipping, clip coefficient}.
+ * Hyper-parameters are doubles, as Python hands them to torch: 1 - beta is formed in double before rounding to fp32.
  * Deterministic; the gradients themselves are left unscaled. */
 long long kz_adam_clip_workspace(int count, const int64_t* numel);
 int kz_adam_clip_step(int count, void* const* params, const void* const* grads, void* const* exp_avg,
-                      void* const* exp_avg_sq, const void* const* steps, const int64_t* numel, float lr, float beta1,
-                      float beta2, float eps, float weight_decay, float max_norm, float* workspace,
+                      void* const* exp_avg_sq, const void* const* steps, const int64_t* numel, double lr, double beta1,
+                      double beta2, double eps, double weight_decay, double max_norm, float* workspace,
                       int64_t workspace_floats, float* norm_out2, void* stream);
 
 #ifdef __cplusplus

@@ -44,7 +44,7 @@ def lib() -> C.CDLL:
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a).  shogidrl_b200 has no CPU fallback.")
     L = C.CDLL(LIB_PATH)
-    vp, i32, i64, u64, u32, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_float
+    vp, i32, i64, u64, u32, f32, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_float, C.c_double
     L.kz_abi_version.restype = i32
     L.kz_last_cuda_error.restype = C.c_char_p
     L.kz_init_tables.argtypes = [vp]
@@ -65,7 +65,7 @@ def lib() -> C.CDLL:
     L.kz_eval_masked_bwd.argtypes = [vp, i32, i64, vp, i64, vp, vp, i32, vp, vp, vp, vp, i64, vp]
     L.kz_eval_masked_bwd_bias.argtypes = [vp, i32, i64, vp, i64, vp, vp, i32, vp, vp, vp, vp, i64, vp, vp]
     L.kz_adam_clip_workspace.argtypes = [i32, vp]
-    L.kz_adam_clip_step.argtypes = [i32, vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, f32, vp, i64, vp, vp]
+    L.kz_adam_clip_step.argtypes = [i32, vp, vp, vp, vp, vp, vp, f64, f64, f64, f64, f64, f64, vp, i64, vp, vp]
     L.kz_obs_conv_fwd.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp]
     L.kz_ppo_loss.argtypes = [vp, vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, vp, vp, vp, vp, vp]
     L.kz_obs_conv_wgrad_ctas.argtypes = [i32]

@@ -103,14 +103,15 @@ __global__ void __launch_bounds__(1024) kz_norm_kernel(const float* __restrict__
 
 struct Hyper {
   float lr, beta1, beta2, eps, weight_decay;
+  float omb1, omb2;  // 1 - beta, formed in double on the host as torch does (1 - 0.999f in fp32 is off by 1.3e-5)
 };
 
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const Hyper& H, float coef, float step_size,
                                          float inv_bc2_sqrt) {
   g *= coef;
   if (H.weight_decay != 0.f) g = fmaf(H.weight_decay, p, g);
-  m = m + (g - m) * (1.0f - H.beta1);                // exp_avg.lerp_(grad, 1 - beta1)
-  v = H.beta2 * v + (1.0f - H.beta2) * (g * g);      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+  m = m + (g - m) * H.omb1;                // exp_avg.lerp_(grad, 1 - beta1)
+  v = H.beta2 * v + H.omb2 * (g * g);      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
   const float denom = sqrtf(v) * inv_bc2_sqrt + H.eps;
   p -= step_size * (m / denom);
 }
@@ -170,14 +171,15 @@ long long kz_adam_clip_workspace(int count, const int64_t* numel) {
 }
 
 int kz_adam_clip_step(int count, void* const* params, const void* const* grads, void* const* exp_avg,
-                      void* const* exp_avg_sq, const void* const* steps, const int64_t* numel, float lr, float beta1,
-                      float beta2, float eps, float weight_decay, float max_norm, float* workspace,
+                      void* const* exp_avg_sq, const void* const* steps, const int64_t* numel, double lr, double beta1,
+                      double beta2, double eps, double weight_decay, double max_norm, float* workspace,
                       int64_t workspace_floats, float* norm_out2, void* stream) {
   if (count <= 0 || !params || !grads || !exp_avg || !exp_avg_sq || !steps || !numel || !workspace || !norm_out2)
     return KZ_E_ARG;
   if (workspace_floats < kz_adam_clip_workspace(count, numel)) return KZ_E_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const Hyper H{lr, beta1, beta2, eps, weight_decay};
+  const Hyper H{(float)lr, (float)beta1, (float)beta2, (float)eps, (float)weight_decay, (float)(1.0 - beta1),
+                (float)(1.0 - beta2)};
   // pass 1 builds the launch groups and runs the partial sums; pass 2 (after the norm) runs Adam on the same groups
   Group groups[64];
   int ngroups = 0, partial0 = 0;
@@ -209,7 +211,7 @@ int kz_adam_clip_step(int count, void* const* params, const void* const* grads, 
   if (ngroups == 0) return KZ_E_ARG;
   for (int k = 0; k < ngroups; k++)
     kz_sumsq_kernel<<<groups[k].blk0[groups[k].count], THREADS, 0, st>>>(groups[k], workspace);
-  kz_norm_kernel<<<1, 1024, 0, st>>>(workspace, partial0, max_norm, norm_out2);
+  kz_norm_kernel<<<1, 1024, 0, st>>>(workspace, partial0, (float)max_norm, norm_out2);
   for (int k = 0; k < ngroups; k++)
     kz_adam_kernel<<<groups[k].blk0[groups[k].count], THREADS, 0, st>>>(groups[k], H, norm_out2);
   cudaError_t e = cudaGetLastError();

@@ -343,12 +343,14 @@ def test_fused_optimizer_tail_matches_torch_optimizer(model_kind):
     # weight gradients and batch-norm statistics are not run-to-run reproducible in bf16: two runs of the SAME optimizer
     # drift by ~0.5 % in the gradient norm over eight updates, so that case only has to stay within a few percent (the
     # exact single-step comparison is tests/test_gpu_rl.py::test_fused_clip_adam_matches_torch).
-    tol, atol = (2e-3, 2e-4) if model_kind == "cnn" else (5e-2, 1.5e-3)
+    # Parameters whose true gradient is zero (a conv bias in front of batch norm) receive rounding noise, which Adam
+    # normalises to +-lr per step, so ResNet parameters are only bounded by the eight steps they can have moved apart.
+    tol, atol = (2e-3, 2e-4) if model_kind == "cnn" else (5e-2, 2 * 8 * 3e-4 + 1e-4)
     for k in ma:
         assert abs(ma[k] - mb_[k]) <= tol * max(1.0, abs(mb_[k])), (k, ma[k], mb_[k])
     assert abs(a.last_gradient_norm - b.last_gradient_norm) <= tol * max(1.0, b.last_gradient_norm)
     for (k, x), y in zip(a.model.named_parameters(), b.model.parameters()):
-        assert torch.allclose(x, y, rtol=tol, atol=atol), (k, float((x - y).abs().max()))
+        assert torch.allclose(x.detach(), y.detach(), rtol=tol, atol=atol), (k, float((x - y).detach().abs().max()))
         sa, sb = a.optimizer.state[x], b.optimizer.state[y]
         assert float(sa["step"]) == float(sb["step"]) == 8
         if model_kind == "cnn":
