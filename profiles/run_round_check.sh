@@ -14,3 +14,8 @@ timeout 300 python profiles/ppo_update_probe.py > $O/ppo_update_breakdown.txt 2>
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $O/launches_ppo.csv \
   python bench.py --workload ppo --steps 1 --warmup 1 --ppo-horizon 8 --ppo-epochs 1 > $O/ncu_ppo.log 2>&1; echo "ncu ppo rc=$?"
 tail -3 $O/pytest_gpu.log; cat $O/smoke.log | tail -2; cat $O/bench.json $O/ppo.json $O/ref.json $O/ref_ppo.json
+# env-step bench under ncu: launch list, then one full-set capture of two kz_step launches (read with ncu_summary.py)
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_env.csv \
+  python bench.py --steps 16 --warmup 3 --no-cpu-baseline > $O/ncu_env.log 2>&1; echo "ncu env rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:kz_step_kernel -s 40 -c 2 -f -o $O/kz_step_final \
+  python bench.py --steps 16 --warmup 3 --no-cpu-baseline > $O/ncu_full.log 2>&1; echo "ncu full rc=$?"

@@ -1,7 +1,7 @@
 #!/bin/bash
 for f in ${VARIANTS:-build/*/*.so}; do
   echo "== $f"
-  KZ_LIB_PATH=$PWD/$f python bench.py --steps 48 --warmup 8 --no-cpu-baseline 2>&1 | python -c "
+  KZ_LIB_PATH=$PWD/$f python bench.py --steps ${STEPS:-128} --warmup 8 --no-cpu-baseline 2>&1 | python -c "
 import sys,json
 for ln in sys.stdin:
     try: d=json.loads(ln)

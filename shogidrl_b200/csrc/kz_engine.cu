@@ -47,6 +47,25 @@ extern __shared__ __align__(16) unsigned char s_dyn[];  // per-warp scratch: WAR
 
 struct Tables {};  // the tables live in s_ray / s_step
 
+// Tuning knobs of the output writers; the defaults are the fastest combination measured on B200
+// (profiles/run_variants.sh builds and times alternatives, profiles/README.md has the table).
+#ifndef KZ_FILL_UNROLL
+#define KZ_FILL_UNROLL 1  // unroll factor of the zero-fill loops
+#endif
+#ifndef KZ_FILL_AFTER_COMPACT
+#define KZ_FILL_AFTER_COMPACT 1  // issue the mask row's zero fill after the from-square compaction (shared-memory reads first)
+#endif
+#ifndef KZ_ST256
+#define KZ_ST256 3  // 256-bit zero-fill stores: bit 0 mask row, bit 1 observation row
+#endif
+constexpr int kFillUnroll = KZ_FILL_UNROLL;
+
+// 32 bytes of zeros with one 256-bit store (STG.E.ENL2.256, sm_100+): half the store instructions of a 128-bit fill
+__device__ __forceinline__ void st_zero256(void* p) {
+  const uint32_t z = 0;
+  asm volatile("st.global.v8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(p), "r"(z) : "memory");
+}
+
 __device__ __forceinline__ BB ld_ray(const Tables&, int sq, int d) {
   const uint32_t* p = s_ray + (sq * 8 + d) * 3;
   return BB{p[0], p[1], p[2]};
@@ -749,6 +768,92 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
       }
     }
 
+    // ---- zero fills of this game's output rows (content-independent; the non-zero entries are overwritten later,
+    // behind a __syncwarp()).  (Issuing them here, ahead of the move generation, was measured slower: +5 % for the mask
+    // row, +15 % for the observation row.)
+    auto fill_mask_zero = [&]() {
+      if (!P.mask || !P.mask_vec) return;
+      uint8_t* mrow = P.mask + (size_t)g * P.mask_stride;
+#if (KZ_ST256 & 1)
+      if ((((uintptr_t)mrow) & 31) == 0) {
+#pragma unroll kFillUnroll
+        for (int q = lane; q < 405; q += 32) st_zero256(mrow + 32 * q);
+        return;
+      }
+#endif
+      uint4* m4 = reinterpret_cast<uint4*>(mrow);
+      const uint4 z4 = make_uint4(0, 0, 0, 0);
+#pragma unroll kFillUnroll
+      for (int q = lane; q < 810; q += 32) m4[q] = z4;
+    };
+    auto fill_obs_zero = [&]() {
+      if (!P.obs) return;
+      float* orow = P.obs + (size_t)g * P.obs_stride;
+#if (KZ_ST256 & 2)
+      // rows are 8-byte aligned: up to three float2 to reach a 32-byte line, 256-bit stores, up to three float2 of tail
+      float2* o2 = reinterpret_cast<float2*>(orow);
+      const int head = (int)(((32u - (unsigned)((uintptr_t)orow & 31)) & 31u) >> 3);
+      const int nb = (KZ_OBS_FLOATS * 4 - head * 8) >> 5;
+      char* body = reinterpret_cast<char*>(orow) + head * 8;
+      if (lane < head) o2[lane] = make_float2(0.f, 0.f);
+#pragma unroll kFillUnroll
+      for (int q = lane; q < nb; q += 32) st_zero256(body + 32 * q);
+      const int tail0 = head + 4 * nb;
+      if (lane < KZ_OBS_FLOATS / 2 - tail0) o2[tail0 + lane] = make_float2(0.f, 0.f);
+#else
+      // float4 chunk q covers floats [mis + 4q, mis + 4q + 4); odd rows start 8 bytes past a 16-byte line
+      const int mis = ((uintptr_t)orow & 15) ? 2 : 0;
+      float4* o4 = reinterpret_cast<float4*>(orow + mis);
+      const float4 zf = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll kFillUnroll
+      for (int q = lane; q < 931; q += 32) o4[q] = zf;
+      if (lane == 0) {  // the 2 floats the float4 grid does not cover: plane 0 head or plane 45 tail, both 0 here
+        float2* o2 = reinterpret_cast<float2*>(orow + (mis ? 0 : 3724));
+        *o2 = make_float2(0.f, 0.f);
+      }
+#endif
+    };
+    auto write_obs = [&]() {
+      if (!P.obs) return;
+      // generate_neural_network_observation (shogi_game_io.py:434-539)
+      float* orow = P.obs + (size_t)g * P.obs_stride;
+      // constant planes 28..45: value of plane 28+i lives in lane i
+      float pv = 0.f;
+      if (lane < 14) {
+        const int cnt = ws.meta[lane < 7 ? side * 7 + lane : (1 - side) * 7 + (lane - 7)];
+        // The reference divides in Python doubles and stores fp32.  For integer operands below 2^16 the exact
+        // quotient is never within 2^-41 (relative) of an fp32 rounding tie, so rounding once (IEEE fp32 division)
+        // and rounding twice (double, then fp32) give the same bits.
+        if (cnt > 0) pv = __fdiv_rn((float)cnt, 18.0f);
+      } else if (lane == 14) pv = side == 0 ? 1.f : 0.f;
+      else if (lane == 15) pv = max_moves > 0 ? __fdiv_rn((float)move_count, (float)max_moves) : 0.f;
+      // Zero-fill the whole row with wide stores, then overwrite what is not zero: the constant planes with a non-zero
+      // value (a few of the 18) and one float per piece.  Both overwrites follow the zero fill in program order behind a
+      // __syncwarp().  (Measured alternatives that were NOT faster: handing the fill to the bulk-copy engine, cp.async.bulk
+      // from a shared zero page; streaming __stcs stores.)
+      fill_obs_zero();
+      __syncwarp();
+      uint32_t nzp = __ballot_sync(FULL, pv != 0.f);  // constant planes 28 + i with a non-zero value
+      while (nzp) {
+        const int i = __ffs(nzp) - 1;
+        nzp &= nzp - 1;
+        const float v = __shfl_sync(FULL, pv, i);
+        float* pl = orow + (28 + i) * 81;
+        pl[lane] = v;
+        pl[lane + 32] = v;
+        if (lane < 17) pl[lane + 64] = v;
+      }
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const int sq = lane + 32 * j;
+        const int code = sq < 81 ? ws.board[sq] : 0;
+        if (code) {
+          const int t = code_type(code), mine = code_color(code) == side;
+          const int plane = t < 8 ? (mine ? 0 : 14) + t : (mine ? 8 : 22) + (t - 8);
+          orow[plane * 81 + (side == 0 ? sq : 80 - sq)] = 1.0f;
+        }
+      }
+    };
     // ---- legal moves of the position now on the board
     // After a legal move the side that just moved is never in check, so a dropped pawn can only give check from
     // the square in front of the enemy king and the specialised test applies.  Loaded positions (refresh mode)
@@ -838,16 +943,15 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
       if (P.in_check) P.in_check[g] = (uint8_t)gr.in_check;
     }
 
-    if (P.mask) {
+    auto write_mask = [&]() {
+      if (!P.mask) return;
       uint8_t* mrow = P.mask + (size_t)g * P.mask_stride;
       if (P.mask_vec) {
         // 16-byte chunk q of the row = bits [16q, 16q+16) of the bitmap; a from-square owns chunks 10f..10f+9.
         // Pass 1 zero-fills the 810 board-move chunks with plain 128-bit stores; pass 2 expands only the chunks
         // of from-squares that have a legal move (3 squares x 10 chunks per warp round) and the 36 drop chunks.
         uint4* m4 = reinterpret_cast<uint4*>(mrow);
-        const uint4 z4 = make_uint4(0, 0, 0, 0);
-#pragma unroll 2
-        for (int q = lane; q < 810; q += 32) m4[q] = z4;
+        if (!KZ_FILL_AFTER_COMPACT) fill_mask_zero();
         uint32_t act[3];
 #pragma unroll
         for (int j = 0; j < 3; j++) {
@@ -865,6 +969,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
           if ((act[j] >> lane) & 1) ws.plist[0][nact + __popc(act[j] & ((1u << lane) - 1))] = (uint8_t)(lane + 32 * j);
           nact += __popc(act[j]);
         }
+        if (KZ_FILL_AFTER_COMPACT) fill_mask_zero();  // after the shared-memory reads above
         __syncwarp();  // orders the zero fill before the overwrites below and publishes plist
         auto expand = [](uint32_t b16) {
           uint4 v;
@@ -896,9 +1001,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
       } else {
         for (int i = lane; i < KZ_NUM_ACTIONS; i += 32) mrow[i] = (uint8_t)((ws.bitmap[i >> 5] >> (i & 31)) & 1);
       }
-    }
-
-    if (P.next_actions) {
+    };
+    auto pick_next = [&]() {
+      if (!P.next_actions) return;
       long long pick = -1;
       if (gr.count > 0) {
         const uint32_t r = rand32(P.seed, (unsigned long long)P.env_offset + (unsigned long long)g, P.rng_step);
@@ -935,58 +1040,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
         if (P.actions_i64) reinterpret_cast<long long*>(P.next_actions)[g] = pick;
         else reinterpret_cast<int*>(P.next_actions)[g] = (int)pick;
       }
-    }
-
-    if (P.obs) {
-      // generate_neural_network_observation (shogi_game_io.py:434-539)
-      float* orow = P.obs + (size_t)g * P.obs_stride;
-      // constant planes 28..45: value of plane 28+i lives in lane i
-      float pv = 0.f;
-      if (lane < 14) {
-        const int cnt = ws.meta[lane < 7 ? side * 7 + lane : (1 - side) * 7 + (lane - 7)];
-        // The reference divides in Python doubles and stores fp32.  For integer operands below 2^16 the exact
-        // quotient is never within 2^-41 (relative) of an fp32 rounding tie, so rounding once (IEEE fp32 division)
-        // and rounding twice (double, then fp32) give the same bits.
-        if (cnt > 0) pv = __fdiv_rn((float)cnt, 18.0f);
-      } else if (lane == 14) pv = side == 0 ? 1.f : 0.f;
-      else if (lane == 15) pv = max_moves > 0 ? __fdiv_rn((float)move_count, (float)max_moves) : 0.f;
-      const int mis = ((uintptr_t)orow & 15) ? 2 : 0;  // rows are 8-byte aligned; odd rows start 8 past a 16-byte line
-      float4* o4 = reinterpret_cast<float4*>(orow + mis);
-      // Zero-fill the whole row with 128-bit stores (float4 chunk q covers floats [mis + 4q, mis + 4q + 4)), then
-      // overwrite what is not zero: the constant planes with a non-zero value (a few of the 18) and one float
-      // per piece.  Both overwrites follow the zero fill in program order behind a __syncwarp().
-      // (Measured alternatives that were NOT faster: issuing this zero fill early, interleaved with the move
-      // application -- 0.476 ms; handing it to the bulk-copy engine, cp.async.bulk from a shared zero page -- 0.469 ms;
-      // streaming __stcs stores -- 0.474 ms; this loop -- 0.457 ms per 65,536-game launch.)
-      const float4 zf = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-      for (int q = lane; q < 931; q += 32) o4[q] = zf;
-      if (lane == 0) {  // the 2 floats the float4 grid does not cover: plane 0 head or plane 45 tail, both 0 here
-        float2* o2 = reinterpret_cast<float2*>(orow + (mis ? 0 : 3724));
-        *o2 = make_float2(0.f, 0.f);
-      }
-      __syncwarp();
-      uint32_t nzp = __ballot_sync(FULL, pv != 0.f);  // constant planes 28 + i with a non-zero value
-      while (nzp) {
-        const int i = __ffs(nzp) - 1;
-        nzp &= nzp - 1;
-        const float v = __shfl_sync(FULL, pv, i);
-        float* pl = orow + (28 + i) * 81;
-        pl[lane] = v;
-        pl[lane + 32] = v;
-        if (lane < 17) pl[lane + 64] = v;
-      }
-#pragma unroll
-      for (int j = 0; j < 3; j++) {
-        const int sq = lane + 32 * j;
-        const int code = sq < 81 ? ws.board[sq] : 0;
-        if (code) {
-          const int t = code_type(code), mine = code_color(code) == side;
-          const int plane = t < 8 ? (mine ? 0 : 14) + t : (mine ? 8 : 22) + (t - 8);
-          orow[plane * 81 + (side == 0 ? sq : 80 - sq)] = 1.0f;
-        }
-      }
-    }
+    };
+    // (Measured and not faster: choosing the next action before the mask row's store burst; writing the observation row
+    // ahead of the move generation, +8 %.)
+    write_mask();
+    pick_next();
+    write_obs();
 
     // ---- store state
     __syncwarp();
