@@ -54,19 +54,28 @@ class VecShogiEnv:
     def _sp(self):
         return nv.stream_ptr(self.device)
 
-    @staticmethod
-    def _obs_args(obs: Optional[torch.Tensor]):
-        if obs is None:
+    def _rows_arg(self, t: Optional[torch.Tensor], what: str, dtypes, row_elems: int):
+        """(data pointer, row stride in elements) of caller storage the kernel writes ``n`` rows into; rejects
+        anything the kernel would write out of bounds (the C ABI sees raw pointers only)."""
+        if t is None:
             return None, 0
-        assert obs.dtype == torch.float32 and obs.stride(-1) == 1
-        return obs.data_ptr(), (obs.stride(0) if obs.dim() > 1 else nv.OBS_FLOATS)
+        if t.device != self.device or t.dtype not in dtypes:
+            raise ValueError(f"{what}: expected a {dtypes[0]} tensor on {self.device}, got {t.dtype} on {t.device}")
+        if t.dim() > 1:
+            rows, stride = t.shape[0], t.stride(0)
+            inner = t[0]
+        else:
+            rows, stride, inner = 1, row_elems, t
+        if rows < self.n or inner.numel() < row_elems or not inner.is_contiguous():
+            raise ValueError(f"{what}: need at least {self.n} rows of {row_elems} contiguous elements, got shape "
+                             f"{tuple(t.shape)} with strides {tuple(t.stride())}")
+        return t.data_ptr(), stride
 
-    @staticmethod
-    def _mask_args(mask: Optional[torch.Tensor]):
-        if mask is None:
-            return None, 0
-        assert mask.dtype in (torch.uint8, torch.bool) and mask.stride(-1) == 1
-        return mask.data_ptr(), (mask.stride(0) if mask.dim() > 1 else nv.NUM_ACTIONS)
+    def _obs_args(self, obs: Optional[torch.Tensor]):
+        return self._rows_arg(obs, "obs", (torch.float32,), nv.OBS_FLOATS)
+
+    def _mask_args(self, mask: Optional[torch.Tensor]):
+        return self._rows_arg(mask, "mask", (torch.uint8, torch.bool), nv.NUM_ACTIONS)
 
     # ------------------------------------------------------------------ API
     def reset(self, env_mask: Optional[torch.Tensor] = None, refresh: bool = True, random_actions: bool = False):
@@ -104,7 +113,10 @@ class VecShogiEnv:
         """make_move for every env.  ``obs`` / ``mask`` may point into a rollout buffer (e.g. obs_buf[t+1]).
         With ``random_actions`` the kernel also writes a uniform-random legal action for the returned state
         into ``next_out`` (default ``self.next_actions``; must not alias ``actions``)."""
-        assert actions.device == self.device and actions.dtype in (torch.int64, torch.int32) and actions.is_contiguous()
+        if (actions.device != self.device or actions.dtype not in (torch.int64, torch.int32)
+                or not actions.is_contiguous() or actions.numel() < self.n):
+            raise ValueError(f"actions: expected {self.n} contiguous int64/int32 policy indices on {self.device}, got "
+                             f"{tuple(actions.shape)} {actions.dtype} on {actions.device}")
         obs = (self.obs if obs is None else obs) if write_obs else None
         mask = (self.mask if mask is None else mask) if write_mask else None
         op, os_ = self._obs_args(obs)
@@ -115,7 +127,8 @@ class VecShogiEnv:
             nxt = self.next_actions if next_out is None else next_out
             if actions.dtype == torch.int32 and nxt.dtype == torch.int64:
                 nxt = nxt.view(torch.int32)[: self.n]
-            assert nxt.data_ptr() != actions.data_ptr()
+            if nxt.data_ptr() == actions.data_ptr():
+                raise ValueError("next_out must not alias actions (the kernel reads one while writing the other)")
         nv.check(self._L.kz_step(self.state.data_ptr(), self.n, self.hist_cap, actions.data_ptr(),
                                  int(actions.dtype == torch.int64), op, os_, mp, ms, self.reward.data_ptr(),
                                  self.done.data_ptr(), self.reason.data_ptr(), self.winner.data_ptr(),

@@ -58,3 +58,27 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.lower() or f == "_never_", (dirpath, f)
+
+
+def test_output_storage_validation_rejects_short_or_misshapen_rows():
+    """The C ABI sees raw pointers, so VecShogiEnv validates caller storage before every launch."""
+    import types
+
+    import pytest
+    import torch
+
+    from shogidrl_b200.vec_env import VecShogiEnv
+
+    env = types.SimpleNamespace(device=torch.device("cpu"), n=4)
+    rows = lambda t, what="obs", dt=(torch.float32,), k=3726: VecShogiEnv._rows_arg(env, t, what, dt, k)
+    assert rows(None) == (None, 0)
+    ok = torch.zeros((4, 46, 9, 9))
+    assert rows(ok) == (ok.data_ptr(), 3726)
+    ring = torch.zeros((3, 4, 46, 9, 9))
+    assert rows(ring[1])[1] == 3726
+    padded = torch.zeros((4, 13536), dtype=torch.uint8)[:, :13527]
+    assert rows(padded, "mask", (torch.uint8, torch.bool), 13527) == (padded.data_ptr(), 13536)
+    for bad in (torch.zeros((3, 46, 9, 9)), torch.zeros((4, 46, 9, 8)), torch.zeros((4, 46, 9, 9), dtype=torch.float64),
+                torch.zeros((4, 9, 9, 46)).permute(0, 3, 1, 2), torch.zeros((46, 9, 9))):
+        with pytest.raises(ValueError):
+            rows(bad)
