@@ -85,6 +85,12 @@ def check(rc: int, what: str) -> None:
         raise NativeError(f"{what} failed: {msg}")
 
 
+def require(cond: bool, what: str) -> None:
+    """Argument validation in front of the raw-pointer C ABI (kept under ``python -O``, unlike ``assert``)."""
+    if not cond:
+        raise ValueError(what)
+
+
 def stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 

@@ -21,7 +21,7 @@ class HostPipelinedEnv:
     def __init__(self, num_envs: int, groups: int = 2, max_moves_per_game: int = 500, device="cuda", seed: int = 1234,
                  env_offset: int = 0, auto_reset: bool = True):
         self.device = nv.require_cuda(device)
-        assert groups >= 1 and num_envs % groups == 0, "num_envs must divide into equal groups"
+        nv.require(groups >= 1 and num_envs % groups == 0, "num_envs must divide into equal groups")
         self.n, self.G, self.ng = int(num_envs), int(groups), int(num_envs) // int(groups)
         self.envs: List[VecShogiEnv] = [
             VecShogiEnv(self.ng, max_moves_per_game, self.device, seed=seed, env_offset=env_offset + g * self.ng,

@@ -24,8 +24,8 @@ class _ObsConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, obs, weight, bias, relu, rows):
         dev = nv.require_cuda(obs.device)
-        assert obs.dtype == torch.float32 and obs.dim() == 4 and tuple(obs.shape[1:]) == (46, 9, 9)
-        assert tuple(weight.shape) == (16, 46, 3, 3)
+        nv.require(obs.dtype == torch.float32 and obs.dim() == 4 and tuple(obs.shape[1:]) == (46, 9, 9), "obs.dtype == torch.float32 and obs.dim() == 4 and tuple(obs.shape[1:]) == (46, 9, 9)")
+        nv.require(tuple(weight.shape) == (16, 46, 3, 3), "tuple(weight.shape) == (16, 46, 3, 3)")
         obs = obs.contiguous()
         if rows is not None:
             rows = rows.contiguous().long()
@@ -126,5 +126,5 @@ class _PolicyHeadEval(torch.autograd.Function):
 def policy_head_evaluate(h: torch.Tensor, linear: torch.nn.Linear, mask: torch.Tensor, actions: torch.Tensor,
                          mask_rows: Optional[torch.Tensor] = None):
     """(log-prob of ``actions``, entropy) of softmax(mask(linear(h))) for a [B, K] feature batch, bf16 GEMMs."""
-    assert linear.out_features == nv.NUM_ACTIONS and mask.stride(-1) == 1 and mask.dtype in (torch.uint8, torch.bool)
+    nv.require(linear.out_features == nv.NUM_ACTIONS and mask.stride(-1) == 1 and mask.dtype in (torch.uint8, torch.bool), "linear.out_features == nv.NUM_ACTIONS and mask.stride(-1) == 1 and mask.dtype in (torch.uint8, torch.bool)")
     return _PolicyHeadEval.apply(h, linear.weight, linear.bias, mask, mask_rows, actions)

@@ -18,9 +18,9 @@ def sample_masked(logits: torch.Tensor, mask: torch.Tensor, seed: int = 0, offse
     Mirrors BaseActorCriticModel.get_action_and_value after forward() (base_actor_critic.py:64-116):
     illegal logits -> -inf, softmax, NaN rows -> uniform, Categorical(probs) with its eps clamp."""
     dev = nv.require_cuda(logits.device)
-    assert logits.dim() == 2 and logits.shape[1] == nv.NUM_ACTIONS and logits.stride(1) == 1
-    assert logits.dtype in (torch.float32, torch.bfloat16)
-    assert mask.shape == logits.shape and mask.stride(1) == 1 and mask.dtype in (torch.uint8, torch.bool)
+    nv.require(logits.dim() == 2 and logits.shape[1] == nv.NUM_ACTIONS and logits.stride(1) == 1, "logits.dim() == 2 and logits.shape[1] == nv.NUM_ACTIONS and logits.stride(1) == 1")
+    nv.require(logits.dtype in (torch.float32, torch.bfloat16), "logits.dtype in (torch.float32, torch.bfloat16)")
+    nv.require(mask.shape == logits.shape and mask.stride(1) == 1 and mask.dtype in (torch.uint8, torch.bool), "mask.shape == logits.shape and mask.stride(1) == 1 and mask.dtype in (torch.uint8, torch.bool)")
     n = logits.shape[0]
     actions = torch.empty(n, dtype=torch.int64, device=dev)
     logp = torch.empty(n, dtype=torch.float32, device=dev)
@@ -92,9 +92,9 @@ def evaluate_masked(logits: torch.Tensor, mask: torch.Tensor, actions: torch.Ten
     """(log_prob of ``actions``, entropy) of the masked softmax over ``logits`` [B, 13527], differentiable w.r.t.
     the logits.  ``mask`` is [B, 13527] (bool/uint8, any row stride) or, with ``mask_rows`` (int64 [B]), the whole
     rollout mask storage indexed per row -- no minibatch gather of masks."""
-    assert logits.dim() == 2 and logits.shape[1] == nv.NUM_ACTIONS and logits.stride(1) == 1
-    assert logits.dtype in (torch.float32, torch.bfloat16)
-    assert mask.stride(-1) == 1 and mask.dtype in (torch.uint8, torch.bool) and mask.dim() == 2
+    nv.require(logits.dim() == 2 and logits.shape[1] == nv.NUM_ACTIONS and logits.stride(1) == 1, "logits.dim() == 2 and logits.shape[1] == nv.NUM_ACTIONS and logits.stride(1) == 1")
+    nv.require(logits.dtype in (torch.float32, torch.bfloat16), "logits.dtype in (torch.float32, torch.bfloat16)")
+    nv.require(mask.stride(-1) == 1 and mask.dtype in (torch.uint8, torch.bool) and mask.dim() == 2, "mask.stride(-1) == 1 and mask.dtype in (torch.uint8, torch.bool) and mask.dim() == 2")
     if mask_rows is not None:
         mask_rows = mask_rows.contiguous().long()
     return _MaskedCategoricalEval.apply(logits, mask, actions, mask_rows)
@@ -108,7 +108,7 @@ class _PPOLoss(torch.autograd.Function):
         dev = nv.require_cuda(new_lp.device)
         n = new_lp.shape[0]
         args = [t.detach().contiguous().float().reshape(-1) for t in (new_lp, entropy, new_v, old_lp, adv, ret)]
-        assert all(t.shape[0] == n for t in args)
+        nv.require(all(t.shape[0] == n for t in args), "all(t.shape[0] == n for t in args)")
         out = torch.empty(6, dtype=torch.float32, device=dev)
         grads = torch.empty((3, n), dtype=torch.float32, device=dev)
         nv.check(nv.lib().kz_ppo_loss(*[t.data_ptr() for t in args], n, float(clip_eps), float(value_coef),
@@ -176,7 +176,7 @@ def adam_clip_step(optimizer: torch.optim.Adam, max_norm: float, norm_out: Optio
     need = int(L.kz_adam_clip_workspace(n, numel))
     ws = torch.empty(max(need, 1), dtype=torch.float32, device=dev)
     out = norm_out if norm_out is not None else torch.empty(2, dtype=torch.float32, device=dev)
-    assert out.numel() >= 2 and out.dtype == torch.float32 and out.is_contiguous()
+    nv.require(out.numel() >= 2 and out.dtype == torch.float32 and out.is_contiguous(), "out.numel() >= 2 and out.dtype == torch.float32 and out.is_contiguous()")
     arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
     b1, b2 = group["betas"]
     nv.check(L.kz_adam_clip_step(n, arr(params), arr(grads), arr([optimizer.state[p]["exp_avg"] for p in params]),

@@ -218,7 +218,8 @@ class VecStepManager:
 
     def __init__(self, env, agent, buffer):
         self.env, self.agent, self.buffer = env, agent, buffer
-        assert buffer.N == env.n
+        if buffer.N != env.n:
+            raise ValueError(f"the rollout buffer holds {buffer.N} games per step but the environment has {env.n}")
         self.episodes = 0
         self.black_wins = self.white_wins = self.draws = 0
         self._started = False

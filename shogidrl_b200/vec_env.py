@@ -148,7 +148,7 @@ class VecShogiEnv:
         if max_moves is None:
             max_moves = np.full(self.n, self.max_moves, np.int32)
         mm = torch.as_tensor(np.ascontiguousarray(max_moves), dtype=torch.int32).to(d).contiguous()
-        assert b.shape == (self.n, 81) and h.shape == (self.n, 14)
+        nv.require(b.shape == (self.n, 81) and h.shape == (self.n, 14), "b.shape == (self.n, 81) and h.shape == (self.n, 14)")
         nv.check(self._L.kz_load_positions(self.state.data_ptr(), self.n, self.hist_cap, b.data_ptr(), h.data_ptr(),
                                            s.data_ptr(), mc.data_ptr(), mm.data_ptr(), self._sp()), "kz_load_positions")
         self.refresh(eval_termination=eval_termination)
@@ -180,7 +180,7 @@ class VecShogiEnv:
     def load_sfens(self, sfens, eval_termination: bool = True):
         """ShogiGame.from_sfen (shogi_game.py:283-345) for a whole batch: one SFEN per env."""
         from .shogi.sfen import pack_sfen
-        assert len(sfens) == self.n
+        nv.require(len(sfens) == self.n, "len(sfens) == self.n")
         packed = [pack_sfen(s) for s in sfens]
         return self.load_positions(np.stack([p[0] for p in packed]), np.stack([p[1] for p in packed]),
                                    np.asarray([p[2] for p in packed], np.uint8), np.asarray([p[3] for p in packed], np.int32),
