@@ -220,6 +220,43 @@ def test_batched_evaluation_games():
     # agent vs agent also runs
     res2 = evaluate_vs_opponent(agent, 16, opponent=agent, num_envs=16, max_moves_per_game=30, deterministic=False)
     assert res2.games >= 16
+    assert len(res.outcomes) == res.games and res.outcomes.count("agent_win") == res.agent_wins
+    assert res.outcomes.count("opponent_win") == res.opponent_wins and res.outcomes.count("draw") == res.draws
+
+
+@pytest.mark.gpu
+def test_tournament_and_ladder_on_the_vectorised_engine():
+    """f-2: tournament standings and a ladder pass whose games run batched on the device (host arithmetic is pinned to
+    the reference in tests/test_evaluation_cpu.py)."""
+    from shogidrl_b200.core import ActorCritic, PPOAgent
+    from shogidrl_b200.evaluation import EloTracker, evaluate_ladder, evaluate_tournament
+    cfg = make_config()
+    torch.manual_seed(5)
+    dev = torch.device("cuda")
+    agent = PPOAgent(ActorCritic(46, 13527), cfg, dev, use_mixed_precision=True)
+    other = PPOAgent(ActorCritic(46, 13527), cfg, dev, use_mixed_precision=True)
+    kw = dict(num_envs=32, max_moves_per_game=40, seed=3, deterministic=False)
+    standings, results = evaluate_tournament(agent, {"random": None, "other": other}, 32, **kw)
+    o = standings["overall_tournament_stats"]
+    assert set(standings["per_opponent_results"]) == {"random", "other"}
+    assert o["total_games"] == sum(r.games for r in results.values()) >= 64
+    assert o["agent_total_wins"] + o["agent_total_losses"] + o["agent_total_draws"] == o["total_games"]
+    for name, r in results.items():
+        row = standings["per_opponent_results"][name]
+        assert (row["played"], row["wins"], row["losses"], row["draws"]) == (r.games, r.agent_wins, r.opponent_wins, r.draws)
+    tracker = EloTracker()
+    tracker.ratings.update({"random": 1400.0, "other": 1500.0, "far": 2200.0})
+    snap, played = evaluate_ladder(agent, "agent", {"random": None, "other": other, "far": other}, tracker,
+                                   num_games_per_match=8, **kw)
+    assert list(played) == ["random", "other"]  # "far" is outside the +-400 window; ascending by rating
+    assert snap["far"] == 2200.0 and set(snap) == {"agent", "random", "other", "far"}
+    expect = EloTracker()
+    expect.ratings.update({"random": 1400.0, "other": 1500.0, "far": 2200.0})
+    for name in played:
+        expect.update_ratings("agent", name, played[name].outcomes)
+    assert snap == expect.get_elo_snapshot()
+    total = sum(snap.values())
+    assert abs(total - (1500.0 + 1400.0 + 1500.0 + 2200.0)) < 1e-6  # Elo updates are zero-sum
 
 
 def test_device_batch_sfen_dump_load_and_kif(golden_dir):
