@@ -1031,6 +1031,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
           return v;
         };
         const int sub = lane / 10, jj = lane - 10 * sub;  // lanes 30, 31 idle in pass 2
+        // (software-pipelining the plist load one round ahead, unrolled by two: measured 0.8 % slower)
 #pragma unroll 1
         for (int base = 0; base < nact; base += 3) {
           const int i = base + sub;
@@ -1082,7 +1083,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
               else rem -= pcs[i];
             }
           }
-          found = (w0 + widx) * 32 + __fns(ws.bitmap[w0 + widx], 0, rem + 1);
+          // rem < popc(wv) and words hold few bits: clear the rem lowest set bits, the next one is the pick (__fns is a
+          // ~50-instruction software routine)
+          uint32_t wv = ws.bitmap[w0 + widx];
+          for (int r = rem; r > 0; r--) wv &= wv - 1;
+          found = (w0 + widx) * 32 + __ffs(wv) - 1;
         }
         const uint32_t who = __ballot_sync(FULL, found >= 0);
         pick = __shfl_sync(FULL, found, __ffs(who) - 1);
