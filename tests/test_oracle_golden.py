@@ -125,3 +125,31 @@ def test_gae_golden(golden_dir):
             assert np.array_equal(ret[:, 0], z[f"c{i}_ret"]), (i, fn.__name__)
     # tests/conftest.py:543-581 known answer
     assert z["c0_adv"][2] == 1.5 and z["c0_ret"][2] == 3.0
+
+
+def test_endgame_traces_bit_exact(golden_dir):
+    """Drop-heavy endgames played by the Python reference (oracle/gen_golden_endgame.py): nifu, drop rank limits,
+    drops answering checks and uchifuzume decide these legal sets (a third of the moves are drops, up to 458 legal
+    moves per position).  Every ply: legal set, action, successor, outcome and observation digest."""
+    with np.load(os.path.join(golden_dir, "traces_endgame.npz")) as zf:
+        z = {k: zf[k] for k in zf.files}
+    base = 0
+    for gi, sfen in enumerate(z["sfens"]):
+        g = orc.OracleGame.from_sfen(str(sfen))
+        b, h, _ = g.export()
+        assert np.array_equal(b, z["start_boards"][gi]) and np.array_equal(h, z["start_hands"][gi]), sfen
+        for t in range(int(z["T"][gi])):
+            i = base + t
+            want = z["legal"][z["legal_off"][i]:z["legal_off"][i + 1]].astype(np.int32)
+            assert np.array_equal(g.legal_indices(), want), (gi, t, sfen)
+            a = g.pick_action(int(z["seed"]), gi, t)
+            assert a == int(z["actions"][i]), (gi, t)
+            reward, done, reason, winner = g.make_move(a)
+            b, h, m = g.export()
+            assert np.array_equal(b, z["boards"][i]) and np.array_equal(h, z["hands"][i]), (gi, t)
+            assert (m[0], m[1]) == (int(z["sides"][i]), int(z["move_counts"][i])), (gi, t)
+            assert (reward, done, reason, winner) == (float(z["rewards"][i]), bool(z["dones"][i]), int(z["reasons"][i]),
+                                                      int(z["winners"][i])), (gi, t)
+            assert _digest(g.observation()) == int(z["digests"][i]), (gi, t)
+        base += int(z["T"][gi])
+    assert base == len(z["actions"]) and int((z["actions"] >= 12960).sum()) > 500
