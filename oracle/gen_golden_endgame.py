@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from gen_golden import REASON_CODE, encode_state, obs_digest, rand32  # noqa: E402
 
 GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
-SEED, N_POS, PLIES = 4242, 64, 36
+SEED, N_POS, PLIES = 4242, 128, 48
 
 
 def random_position(rng):

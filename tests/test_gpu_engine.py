@@ -99,6 +99,50 @@ def test_golden_traces_replay(traces):
     assert total == len(z["actions"])
 
 
+def test_golden_endgame_traces_replay(golden_dir):
+    """Drop-heavy endgames played by the Python reference (oracle/gen_golden_endgame.py), replayed on the GPU in one
+    batch loaded from the fixture's SFENs: legal masks before every ply, successor boards / hands / side / move count,
+    reward, done, reason, winner and the observation digest after it.  Games that ended early idle on a finished
+    position (make_move then returns the terminal tuple again) and are no longer compared."""
+    from shogidrl_b200 import VecShogiEnv
+
+    with np.load(os.path.join(golden_dir, "traces_endgame.npz")) as zf:
+        z = {k: zf[k] for k in zf.files}
+    dev = torch.device("cuda:0")
+    n = len(z["sfens"])
+    starts = np.concatenate([[0], np.cumsum(z["T"])])[:-1]
+    env = VecShogiEnv(n, max_moves_per_game=500, device=dev, auto_reset=False)
+    env.load_sfens([str(s) for s in z["sfens"]])
+    b, h, _ = [x.cpu().numpy() for x in env.export()]
+    assert np.array_equal(b, z["start_boards"]) and np.array_equal(h, z["start_hands"])
+    plies = 0
+    for t in range(int(z["T"].max())):
+        live = np.nonzero(z["T"] > t)[0]
+        ix = starts[live] + t
+        mask = env.mask.cpu().numpy()
+        b, h, m = [x.cpu().numpy() for x in env.export()]
+        for e, i in zip(live, ix):
+            want = z["legal"][z["legal_off"][i]:z["legal_off"][i + 1]].astype(np.int64)
+            got = np.nonzero(mask[e])[0]
+            assert np.array_equal(got, want), (e, t, _explain(b[e], h[e], m[e, 0], got, want))
+        acts = np.zeros(n, np.int64)
+        acts[live] = z["actions"][ix]
+        out = env.step(torch.as_tensor(acts, device=dev))
+        b, h, m = [x.cpu().numpy() for x in env.export()]
+        obs = out["obs"].cpu().numpy()
+        assert np.array_equal(b[live], z["boards"][ix]) and np.array_equal(h[live], z["hands"][ix]), t
+        assert np.array_equal(m[live, 0], z["sides"][ix]) and np.array_equal(m[live, 1], z["move_counts"][ix]), t
+        assert np.array_equal(out["reward"].cpu().numpy()[live], z["rewards"][ix]), t
+        assert np.array_equal(out["done"].cpu().numpy()[live], z["dones"][ix]), t
+        assert np.array_equal(out["reason"].cpu().numpy()[live], z["reasons"][ix]), t
+        assert np.array_equal(out["winner"].cpu().numpy()[live], z["winners"][ix]), t
+        for e, i in zip(live, ix):
+            assert _digest(obs[e]) == int(z["digests"][i]), (e, t)
+        assert int(env.errors()[torch.as_tensor(live, device=dev)].abs().sum()) == 0
+        plies += len(live)
+    assert plies == len(z["actions"]) and int((z["actions"] >= 12960).sum()) > 1000
+
+
 def test_golden_full_observations(traces):
     """Raw observation tensors (not only digests) at the sampled plies."""
     from shogidrl_b200 import VecShogiEnv
