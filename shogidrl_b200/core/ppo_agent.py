@@ -185,7 +185,9 @@ class PPOAgent:
         if self.scheduler is not None and self.lr_schedule_step_on == "epoch":
             self.scheduler.step()
         avg = (self._sums / max(1, updates)).tolist()  # one host synchronisation per learn() instead of 5 per minibatch
-        self.last_gradient_norm = float(self._gn) if updates else 0.0
+        # the reference reports the norm of the gradients AFTER clipping (ppo_agent.py:395-401 / 409-415)
+        gn = float(self._gn) if updates else 0.0
+        self.last_gradient_norm = gn * min(1.0, self.gradient_clip_max_norm / (gn + 1e-6))
         self.last_kl_div = avg[3]
         return {"ppo/policy_loss": avg[0], "ppo/value_loss": avg[1], "ppo/entropy": avg[2],
                 "ppo/kl_divergence_approx": avg[3], "ppo/clip_fraction": avg[4],

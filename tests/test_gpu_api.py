@@ -208,6 +208,72 @@ def test_parallel_manager_shim():
     assert not pm.is_healthy() and pm.get_parallel_stats()["total_steps_collected"] == 64
 
 
+def test_agent_matches_reference_golden(golden_dir):
+    """SURVEY 8a-13 / 8a-14 / 8f-1 against the Python reference itself (oracle/gen_golden_agent.py, CPU fp32): same
+    deterministic weights loaded through the reference's parameter names, same buffer contents; deterministic action
+    selection, evaluate_actions, GAE and one PPOAgent.learn() (2 epochs x 1 minibatch: fused evaluation, loss and
+    clip + Adam kernels on this side) must reproduce the reference's outputs.  fp32 on both sides, TF32 off;
+    tolerances cover summation order only."""
+    from oracle.gen_golden_agent import TRAINING, det_state_dict
+    from shogidrl_b200.core import ActorCritic, ExperienceBuffer, PPOAgent
+    with np.load(os.path.join(golden_dir, "agent_golden.npz")) as zf:
+        z = {k: zf[k] for k in zf.files}
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        dev = torch.device("cuda")
+        n = int(z["n"])
+        model = ActorCritic(46, 13527)
+        model.load_state_dict(det_state_dict())  # strict: the reference's parameter names and shapes
+        agent = PPOAgent(model, make_config(**TRAINING), dev, use_mixed_precision=False)
+        obs = torch.as_tensor(z["obs"], device=dev)
+        masks = torch.zeros((n, 13527), dtype=torch.bool, device=dev)
+        for i in range(n):
+            masks[i, torch.as_tensor(z["legal"][z["legal_off"][i]:z["legal_off"][i + 1]].astype(np.int64), device=dev)] = True
+        # a-13: deterministic selection and values
+        a, lp, v = agent.select_actions(obs, masks, is_training=False)
+        assert np.array_equal(a.cpu().numpy(), z["det_actions"])
+        np.testing.assert_allclose(lp.cpu().numpy(), z["det_log_probs"], rtol=0, atol=2e-5)
+        np.testing.assert_allclose(v.cpu().numpy(), z["det_values"], rtol=0, atol=2e-5)
+        # evaluate_actions (log-prob of the taken actions, entropy over legal actions, values)
+        model.eval()
+        with torch.no_grad():
+            elp, ent, ev = model.evaluate_actions(obs, torch.as_tensor(z["actions"], device=dev), masks)
+        np.testing.assert_allclose(elp.cpu().numpy(), z["ev_log_probs"], rtol=0, atol=2e-5)
+        np.testing.assert_allclose(ent.cpu().numpy(), z["ev_entropy"], rtol=0, atol=2e-5)
+        np.testing.assert_allclose(ev.cpu().numpy().reshape(-1), z["ev_values"], rtol=0, atol=2e-5)
+        # a-14: buffer + GAE (bit-exact: the inputs are the reference's own fp32 numbers)
+        buf = ExperienceBuffer(n, TRAINING["gamma"], TRAINING["lambda_gae"], "cuda")
+        for i in range(n):
+            buf.add(obs[i], int(z["actions"][i]), float(z["rewards"][i]), float(z["log_probs"][i]), float(z["values"][i]),
+                    bool(z["dones"][i]), masks[i])
+        buf.compute_advantages_and_returns(float(z["last_value"]))
+        batch = buf.get_batch()
+        assert np.array_equal(batch["advantages"].cpu().numpy(), z["advantages"])
+        assert np.array_equal(batch["returns"].cpu().numpy(), z["returns"])
+        # f-1: one learn() call
+        before = {k: t.detach().clone() for k, t in model.state_dict().items()}
+        metrics = agent.learn(buf)
+        want = dict(zip([str(k) for k in z["metric_names"]], z["metric_values"]))
+        for k, w in want.items():
+            assert abs(metrics[k] - w) <= 2e-5 + 1e-3 * abs(w), (k, metrics[k], w)
+        assert abs(agent.last_gradient_norm - float(z["last_gradient_norm"])) < 1e-4
+        after = model.state_dict()
+        lr = TRAINING["learning_rate"]
+        for k in before:
+            delta = (after[k] - before[k]).cpu().numpy().reshape(-1)
+            nnz, abs_sum, _ = z[f"delta_stats/{k}"]
+            # Adam's first steps move every parameter with a gradient by ~lr per step whatever the gradient's size, so
+            # entries whose gradient is pure rounding noise can differ; everything else must agree closely
+            got, ref = delta[z[f"delta_idx/{k}"]], z[f"delta_val/{k}"]
+            close = np.abs(got - ref) <= 0.1 * lr
+            assert close.mean() > 0.97, (k, float(close.mean()))
+            assert abs(np.abs(delta).sum(dtype=np.float64) - abs_sum) <= 0.01 * abs_sum, (k, abs_sum)
+            assert abs(int(np.count_nonzero(delta)) - int(nnz)) <= 0.01 * nnz + 1, (k, int(np.count_nonzero(delta)), nnz)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
 def test_batched_evaluation_games():
     from shogidrl_b200.core import ActorCritic, PPOAgent
     from shogidrl_b200.evaluation import evaluate_vs_opponent
