@@ -274,6 +274,25 @@ def test_agent_matches_reference_golden(golden_dir):
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
 
 
+def test_step_manager_matches_reference_golden(golden_dir):
+    """the reference's StepManager driven over its own ShogiGame / PolicyOutputMapper / ExperienceBuffer
+    by a scripted agent (oracle/gen_golden_stepmanager.py) against the same loop over this repo's classes on the
+    device: every StepResult, counter, EpisodeState, episode-end log line and W&B payload, and the buffer contents."""
+    import json
+    from oracle.gen_golden_stepmanager import drive
+    from shogidrl_b200.core import ExperienceBuffer
+    from shogidrl_b200.shogi import ShogiGame
+    from shogidrl_b200.training import StepManager
+    from shogidrl_b200.utils import PolicyOutputMapper
+    with open(os.path.join(golden_dir, "stepmanager_golden.json")) as f:
+        want = json.load(f)
+    got = json.loads(json.dumps(drive(StepManager, ShogiGame, PolicyOutputMapper, ExperienceBuffer, "cuda")))
+    assert got["ends"] == want["ends"] and len(want["ends"]) == 3
+    for t, (g, w) in enumerate(zip(got["steps"], want["steps"])):
+        assert g == w, (t, g, w)
+    assert got["buffer"] == want["buffer"] and got["n_logs"] == want["n_logs"]
+
+
 def test_batched_evaluation_games():
     from shogidrl_b200.core import ActorCritic, PPOAgent
     from shogidrl_b200.evaluation import evaluate_vs_opponent
