@@ -121,7 +121,6 @@ class VecShogiEnv:
         mask = (self.mask if mask is None else mask) if write_mask else None
         op, os_ = self._obs_args(obs)
         mp, ms = self._mask_args(mask)
-        self.step_index += 1
         nxt = None
         if random_actions:
             nxt = self.next_actions if next_out is None else next_out
@@ -129,6 +128,7 @@ class VecShogiEnv:
                 nxt = nxt.view(torch.int32)[: self.n]
             if nxt.data_ptr() == actions.data_ptr():
                 raise ValueError("next_out must not alias actions (the kernel reads one while writing the other)")
+        self.step_index += 1  # after validation: a rejected call leaves the RNG counter where it was
         nv.check(self._L.kz_step(self.state.data_ptr(), self.n, self.hist_cap, actions.data_ptr(),
                                  int(actions.dtype == torch.int64), op, os_, mp, ms, self.reward.data_ptr(),
                                  self.done.data_ptr(), self.reason.data_ptr(), self.winner.data_ptr(),

@@ -493,3 +493,27 @@ def test_full_size_stress_properties():
     assert torch.equal(env.obs, obs_k) and torch.equal(env.mask, mask_k)       # refresh == what the step kernel wrote
     r = reasons.tolist()
     assert r[1] > 0 and r[3] > 0 and r[4] > 0, r                               # checkmates, truncations and sennichite all occur
+
+
+def test_storage_and_action_validation_on_a_live_env():
+    """The Python layer refuses storage the kernel would overrun or mis-stride (the C ABI only sees pointers)."""
+    from shogidrl_b200 import VecShogiEnv
+
+    dev = torch.device("cuda:0")
+    env = VecShogiEnv(8, device=dev)
+    good = torch.zeros(8, dtype=torch.int64, device=dev)
+    for bad in (torch.zeros(7, dtype=torch.int64, device=dev), torch.zeros(8, dtype=torch.float32, device=dev),
+                torch.zeros(16, dtype=torch.int64, device=dev)[::2], torch.zeros(8, dtype=torch.int64)):
+        with pytest.raises(ValueError):
+            env.step(bad)
+    with pytest.raises(ValueError):
+        env.step(good, obs=torch.zeros((7, 46, 9, 9), device=dev))
+    with pytest.raises(ValueError):
+        env.step(good, mask=torch.zeros((8, 13000), dtype=torch.uint8, device=dev))
+    with pytest.raises(ValueError):
+        env.refresh(obs=torch.zeros((8, 46, 9, 9), dtype=torch.float64, device=dev))
+    with pytest.raises(ValueError):
+        env.step(good, random_actions=True, next_out=good)
+    assert int(env.errors().abs().sum()) == 0 and env.step_index == 0  # nothing was launched
+    out = env.step(torch.full((8,), 13526 + 1, dtype=torch.int64, device=dev))  # out-of-range index: per-env error bit
+    assert int(out["done"].sum()) == 0 and bool((env.errors() & 1).all())
