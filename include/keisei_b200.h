@@ -117,6 +117,19 @@ int kz_step(void* state, int n, int hist_cap, const void* actions, int actions_i
             uint8_t* reason, int8_t* winner, int32_t* ep_len, int32_t* legal_count, void* next_actions,
             uint64_t seed, uint32_t rng_step, uint32_t env_offset, int auto_reset, void* stream);
 
+/* Split pipeline (experimental; same results as kz_step, bit for bit): kz_step_compact is kz_step without the two row
+ * outputs -- it leaves the successor's 13,527-bit legal bitmap in bitmap [n][448] uint32 (bit i of the row = action i;
+ * 16-byte aligned) -- and kz_expand writes the mask and observation rows of the CURRENT positions from the state and
+ * that bitmap (PolicyOutputMapper.get_legal_mask, utils.py:310-336; generate_neural_network_observation,
+ * shogi_game_io.py:434-539).  Meant for two groups of games on two streams: one group's row stores then overlap the
+ * other group's move generation instead of stalling it. */
+int kz_step_compact(void* state, int n, int hist_cap, const void* actions, int actions_i64, uint32_t* bitmap,
+                    float* reward, uint8_t* done, uint8_t* reason, int8_t* winner, int32_t* ep_len, int32_t* legal_count,
+                    void* next_actions, uint64_t seed, uint32_t rng_step, uint32_t env_offset, int auto_reset,
+                    void* stream);
+int kz_expand(const void* state, int n, int hist_cap, const uint32_t* bitmap, float* obs, int64_t obs_stride,
+              uint8_t* mask, int64_t mask_stride, void* stream);
+
 /* Thin conveniences over kz_refresh. */
 int kz_legal_mask(void* state, int n, int hist_cap, uint8_t* mask, int64_t mask_stride,
                   int32_t* legal_count, void* stream);

@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("KZ_LIB_PATH") or os.path.join(_HERE, "libkeisei_b200.
 NUM_ACTIONS = 13527
 OBS_FLOATS = 46 * 81
 MASK_PAD_STRIDE = 13536
+BITMAP_WORDS = 448
 REASONS = {0: None, 1: "Tsumi", 2: "stalemate", 3: "Max moves reached", 4: "Sennichite"}
 
 EXPORTS = [
@@ -23,6 +24,7 @@ EXPORTS = [
     "kz_export_positions", "kz_piece_targets", "kz_refresh", "kz_step", "kz_legal_mask", "kz_observe", "kz_errors", "kz_sample_masked",
     "kz_gae", "kz_gae_exact", "kz_eval_masked_fwd", "kz_eval_masked_bwd", "kz_obs_conv_fwd", "kz_obs_conv_wgrad_ctas",
     "kz_obs_conv_wgrad", "kz_ppo_loss", "kz_eval_masked_bwd_bias", "kz_adam_clip_workspace", "kz_adam_clip_step",
+    "kz_step_compact", "kz_expand",
 ]
 
 
@@ -54,6 +56,8 @@ def lib() -> C.CDLL:
     L.kz_export_positions.argtypes = [vp, i32, i32, vp, vp, vp, vp]
     L.kz_refresh.argtypes = [vp, i32, i32, vp, i64, vp, i64, vp, vp, i32, u64, u32, u32, i32, vp, vp]
     L.kz_step.argtypes = [vp, i32, i32, vp, i32, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, vp]
+    L.kz_step_compact.argtypes = [vp, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, vp]
+    L.kz_expand.argtypes = [vp, i32, i32, vp, vp, i64, vp, i64, vp]
     L.kz_legal_mask.argtypes = [vp, i32, i32, vp, i64, vp, vp]
     L.kz_observe.argtypes = [vp, i32, i32, vp, i64, vp]
     L.kz_errors.argtypes = [vp, i32, i32, vp, i32, vp]

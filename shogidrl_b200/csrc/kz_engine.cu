@@ -576,6 +576,7 @@ struct StepParams {
   int mode;  // 0 = refresh, 1 = step
   int eval_term;
   int* tile_counter;  // zeroed per launch: tiles (8 games, one per warp) beyond the first are claimed dynamically
+  uint32_t* bitmap_out;  // mode 2: the legal bitmap [n][BITMAP_WORDS] instead of the mask / observation rows
 };
 
 __device__ __forceinline__ uint32_t rand32(unsigned long long seed, unsigned long long env, unsigned long long step) {
@@ -589,6 +590,8 @@ __device__ __forceinline__ uint32_t rand32(unsigned long long seed, unsigned lon
 __device__ __forceinline__ uint16_t ld_u16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
 __device__ __forceinline__ void st_u16(uint8_t* p, int v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
 
+// MODE 2 = step for the split pipeline (kz_step_compact): as MODE 1, but the rows are left to kz_expand_kernel and the
+// 13,527-bit legal bitmap is written out instead.
 // MODE 1 = step (the hot kernel: only the fast paths are compiled in, the generator is inlined), MODE 0 = refresh
 // (loaded positions: nested-generation uchifuzume, full key, optional termination evaluation).
 template <int MODE>
@@ -613,7 +616,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
                      : reinterpret_cast<const uint32_t*>(P.meta + (size_t)g * 32)[lane - 24];
   };
   auto fetch_action = [&](int g) -> long long {
-    if (g >= P.n || MODE != 1) return 0;
+    if (g >= P.n || MODE == 0) return 0;
     return P.actions_i64 ? reinterpret_cast<const long long*>(P.actions)[g]
                          : (long long)reinterpret_cast<const int*>(P.actions)[g];
   };
@@ -675,7 +678,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
     bool probe = false;  // a repetition-table probe is in flight (first window of 32 slots in probe_e)
     uint4 probe_e = make_uint4(0, 0, 0, 0);
 
-    if (MODE == 1) {
+    if (MODE != 0) {
       if (status != 0) {
         // make_move on a finished game returns the terminal tuple again (shogi_game.py:589-593)
       } else if (a < 0 || a >= KZ_NUM_ACTIONS) {
@@ -883,7 +886,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
     // when that king is attacked.
     if (MODE == 0) key = position_key(ws, lane, side);  // loaded positions: full key
     GenResult gr;
-    if constexpr (MODE == 1) {
+    if constexpr (MODE != 0) {
       gr = gen_moves_impl<true, UFZ_FAST>(tab, side, UFZ_FAST);  // inlined, fast uchifuzume path only
     } else {
       int mode = UFZ_GENERIC;
@@ -927,7 +930,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
       } else if (move_count >= max_moves) { status = KZ_MAX_MOVES; winner = -1; }
       else if (fresh_senn) { status = KZ_SENNICHITE; winner = -1; }
     }
-    if (MODE == 1 && status != 0) {  // _handle_real_move_return (shogi_game.py:553-572)
+    if (MODE != 0 && status != 0) {  // _handle_real_move_return (shogi_game.py:553-572)
       done_out = 1;
       reason_out = status;
       winner_out = winner;
@@ -935,7 +938,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
       if (winner >= 0) reward = winner == mover ? 1.f : -1.f;
     }
 
-    if (MODE == 1 && status != 0 && P.auto_reset) {
+    if (MODE != 0 && status != 0 && P.auto_reset) {
       // StepManager.handle_episode_end -> game.reset() (step_manager.py:437-440; shogi_game.py:113-130)
       __syncwarp();
       if (lane < 24) reinterpret_cast<uint32_t*>(ws.board)[lane] = reinterpret_cast<const uint32_t*>(c_init_board)[lane];
@@ -1099,9 +1102,16 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
     };
     // (Measured and not faster: choosing the next action before the mask row's store burst; writing the observation row
     // ahead of the move generation, +8 %.)
-    write_mask();
-    pick_next();
-    write_obs();
+    if constexpr (MODE == 2) {
+      __syncwarp();
+      uint4* dst = reinterpret_cast<uint4*>(P.bitmap_out + (size_t)g * BITMAP_WORDS);
+      for (int i = lane; i < BITMAP_WORDS / 4; i += 32) dst[i] = reinterpret_cast<const uint4*>(ws.bitmap)[i];
+      pick_next();
+    } else {
+      write_mask();
+      pick_next();
+      write_obs();
+    }
 
     // ---- store state
     __syncwarp();
@@ -1134,6 +1144,99 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the zero page must outlive the copies that read it
 #endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// Split pipeline, second half: the mask and observation rows of n games from their state rows and legal bitmaps.  Pure
+// streaming work (1.9 KB read, 28.4 KB written per game, no dependent shared-memory chains): it is meant to run on its
+// own stream next to kz_step_kernel<2> of another group of games, so that generating warps never wait behind row stores.
+#ifndef KZ_EXPAND_CTAS_PER_SM
+#define KZ_EXPAND_CTAS_PER_SM 1
+#endif
+#ifndef KZ_COMPACT_CTAS_PER_SM
+#define KZ_COMPACT_CTAS_PER_SM 2  // leaves registers for one expander CTA per SM beside the generating CTAs
+#endif
+__global__ void __launch_bounds__(256) kz_expand_kernel(const uint8_t* __restrict__ boards, const uint8_t* __restrict__ meta,
+                                                        const uint32_t* __restrict__ bitmap, int n, float* obs,
+                                                        long long obs_stride, uint8_t* mask, long long mask_stride,
+                                                        int mask_vec) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto expand = [](uint32_t b16) {
+    uint4 v;
+    v.x = ((b16 & 0xF) * 0x00204081u) & 0x01010101u;
+    v.y = (((b16 >> 4) & 0xF) * 0x00204081u) & 0x01010101u;
+    v.z = (((b16 >> 8) & 0xF) * 0x00204081u) & 0x01010101u;
+    v.w = (((b16 >> 12) & 0xF) * 0x00204081u) & 0x01010101u;
+    return v;
+  };
+  for (int g = blockIdx.x * 8 + warp; g < n; g += gridDim.x * 8) {
+    const uint32_t* bm = bitmap + (size_t)g * BITMAP_WORDS;
+    if (mask) {
+      uint8_t* mrow = mask + (size_t)g * mask_stride;
+      if (mask_vec) {
+        uint4* m4 = reinterpret_cast<uint4*>(mrow);
+#pragma unroll 4
+        for (int q = lane; q < 846; q += 32) {  // chunk q = bits [16q, 16q + 16): every chunk is written, no zero fill
+          const uint32_t w = __ldg(bm + (q >> 1));
+          const uint4 v = expand((q & 1) ? (w >> 16) : (w & 0xFFFF));
+          if (q < 845 || mask_stride >= 13536) m4[q] = v;
+          else {  // last 7 bytes of an exactly-13,527-byte aligned row
+            const uint32_t parts[2] = {v.x, v.y};
+            for (int b = 0; b < 7; b++) mrow[13520 + b] = (uint8_t)(parts[b >> 2] >> (8 * (b & 3)));
+          }
+        }
+      } else {
+        for (int i = lane; i < KZ_NUM_ACTIONS; i += 32) mrow[i] = (uint8_t)((__ldg(bm + (i >> 5)) >> (i & 31)) & 1);
+      }
+    }
+    if (obs) {
+      // generate_neural_network_observation (shogi_game_io.py:434-539), as the tail of kz_step_kernel writes it
+      float* orow = obs + (size_t)g * obs_stride;
+      const uint8_t* b = boards + (size_t)g * 96;
+      const uint8_t* m = meta + (size_t)g * 32;
+      const int side = m[14];
+      const int move_count = m[18] | (m[19] << 8), max_moves = m[22] | (m[23] << 8);
+      float pv = 0.f;
+      if (lane < 14) {
+        const int cnt = m[lane < 7 ? side * 7 + lane : (1 - side) * 7 + (lane - 7)];
+        if (cnt > 0) pv = __fdiv_rn((float)cnt, 18.0f);
+      } else if (lane == 14) pv = side == 0 ? 1.f : 0.f;
+      else if (lane == 15) pv = max_moves > 0 ? __fdiv_rn((float)move_count, (float)max_moves) : 0.f;
+      int code3[3];
+#pragma unroll
+      for (int j = 0; j < 3; j++) { const int sq = lane + 32 * j; code3[j] = sq < 81 ? b[sq] : 0; }
+      float2* o2 = reinterpret_cast<float2*>(orow);
+      const int head = (int)(((32u - (unsigned)((uintptr_t)orow & 31)) & 31u) >> 3);
+      const int nb = (KZ_OBS_FLOATS * 4 - head * 8) >> 5;
+      char* body = reinterpret_cast<char*>(orow) + head * 8;
+      if (lane < head) o2[lane] = make_float2(0.f, 0.f);
+#pragma unroll 4
+      for (int q = lane; q < nb; q += 32) st_zero256(body + 32 * q);
+      const int tail0 = head + 4 * nb;
+      if (lane < KZ_OBS_FLOATS / 2 - tail0) o2[tail0 + lane] = make_float2(0.f, 0.f);
+      __syncwarp();  // the overwrites below follow the zero fill in program order
+      uint32_t nzp = __ballot_sync(FULL, pv != 0.f);
+      while (nzp) {
+        const int i = __ffs(nzp) - 1;
+        nzp &= nzp - 1;
+        const float v = __shfl_sync(FULL, pv, i);
+        float* pl = orow + (28 + i) * 81;
+        pl[lane] = v;
+        pl[lane + 32] = v;
+        if (lane < 17) pl[lane + 64] = v;
+      }
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const int sq = lane + 32 * j;
+        const int code = code3[j];
+        if (code) {
+          const int t = code_type(code), mine = code_color(code) == side;
+          const int plane = t < 8 ? (mine ? 0 : 14) + t : (mine ? 8 : 22) + (t - 8);
+          orow[plane * 81 + (side == 0 ? sq : 80 - sq)] = 1.0f;
+        }
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1295,7 +1398,7 @@ int launch_step(void* state, int n, int hist_cap, StepParams P, cudaStream_t st)
     if (n == 1 && ((uintptr_t)P.mask & 15) == 0) P.mask_vec = 1;
   }
   const int ctas_needed = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-  int grid = g_sm_count * CTAS_PER_SM;
+  int grid = g_sm_count * (P.mode == 2 ? KZ_COMPACT_CTAS_PER_SM : CTAS_PER_SM);
   if (grid > ctas_needed) grid = ctas_needed;
   const size_t dyn = sizeof(WarpScratch) * WARPS_PER_CTA;
   P.tile_counter = nullptr;
@@ -1307,6 +1410,7 @@ int launch_step(void* state, int n, int hist_cap, StepParams P, cudaStream_t st)
   }
 #endif
   if (P.mode == 1) kz_step_kernel<1><<<grid, WARPS_PER_CTA * 32, dyn, st>>>(P);
+  else if (P.mode == 2) kz_step_kernel<2><<<grid, WARPS_PER_CTA * 32, dyn, st>>>(P);
   else kz_step_kernel<0><<<grid, WARPS_PER_CTA * 32, dyn, st>>>(P);
   CK(cudaGetLastError());
   return KZ_OK;
@@ -1401,6 +1505,7 @@ int kz_init_tables(void* stream) {
     const int dyn = (int)(sizeof(WarpScratch) * WARPS_PER_CTA);
     CK(cudaFuncSetAttribute(kz_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
     CK(cudaFuncSetAttribute(kz_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    CK(cudaFuncSetAttribute(kz_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
   }
   g_host_ready = true;
   // legal bitmap of the start position, computed once by the engine itself on a scratch game
@@ -1507,6 +1612,42 @@ int kz_step(void* state, int n, int hist_cap, const void* actions, int actions_i
   P.seed = seed; P.rng_step = rng_step; P.env_offset = env_offset;
   P.auto_reset = auto_reset; P.mode = 1;
   return launch_step(state, n, hist_cap, P, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int kz_step_compact(void* state, int n, int hist_cap, const void* actions, int actions_i64, uint32_t* bitmap,
+                    float* reward, uint8_t* done, uint8_t* reason, int8_t* winner, int32_t* ep_len, int32_t* legal_count,
+                    void* next_actions, uint64_t seed, uint32_t rng_step, uint32_t env_offset, int auto_reset,
+                    void* stream) {
+  if (!actions || !bitmap || ((uintptr_t)bitmap & 15)) return KZ_E_ARG;
+  StepParams P{};
+  P.actions = actions; P.actions_i64 = actions_i64;
+  P.bitmap_out = bitmap;
+  P.reward = reward; P.done = done; P.reason = reason; P.winner = winner; P.ep_len = ep_len;
+  P.legal_count = legal_count; P.next_actions = next_actions;
+  P.seed = seed; P.rng_step = rng_step; P.env_offset = env_offset;
+  P.auto_reset = auto_reset; P.mode = 2;
+  return launch_step(state, n, hist_cap, P, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int kz_expand(const void* state, int n, int hist_cap, const uint32_t* bitmap, float* obs, int64_t obs_stride,
+              uint8_t* mask, int64_t mask_stride, void* stream) {
+  if (!state || n <= 0 || hist_cap < 0 || hist_cap > 65535 || !bitmap || (!obs && !mask)) return KZ_E_ARG;
+  if (!g_host_ready) return KZ_E_NOT_INIT;
+  if (obs && ((((uintptr_t)obs) & 15) || (obs_stride & 1) || obs_stride < KZ_OBS_FLOATS)) return KZ_E_ARG;
+  int mask_vec = 0;
+  if (mask) {
+    if (mask_stride < KZ_NUM_ACTIONS) return KZ_E_ARG;
+    mask_vec = ((((uintptr_t)mask) & 15) == 0 && (mask_stride & 15) == 0) ? 1 : 0;
+    if (n == 1 && (((uintptr_t)mask) & 15) == 0) mask_vec = 1;
+  }
+  const Layout L = layout(n, hist_cap);
+  const uint8_t* base = reinterpret_cast<const uint8_t*>(state);
+  int grid = g_sm_count * KZ_EXPAND_CTAS_PER_SM;
+  if (grid > (n + 7) / 8) grid = (n + 7) / 8;
+  kz_expand_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(base + L.off_boards, base + L.off_meta, bitmap, n,
+                                                                            obs, obs_stride, mask, mask_stride, mask_vec);
+  CK(cudaGetLastError());
+  return KZ_OK;
 }
 
 int kz_legal_mask(void* state, int n, int hist_cap, uint8_t* mask, int64_t mask_stride, int32_t* legal_count,

@@ -138,6 +138,54 @@ class VecShogiEnv:
         return {"obs": obs, "mask": mask, "reward": self.reward, "done": self.done, "reason": self.reason,
                 "winner": self.winner, "ep_len": self.ep_len, "legal_count": self.legal_count}
 
+    def step_compact(self, actions: torch.Tensor, bitmap: Optional[torch.Tensor] = None, random_actions: bool = False,
+                     next_out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """First half of the split pipeline (kz_step_compact): ``step`` without the mask / observation rows; the
+        successor's legal bitmap goes to ``bitmap`` (int32 [n, 448], default ``self.bitmap``) for ``expand``."""
+        if (actions.device != self.device or actions.dtype not in (torch.int64, torch.int32)
+                or not actions.is_contiguous() or actions.numel() < self.n):
+            raise ValueError(f"actions: expected {self.n} contiguous int64/int32 policy indices on {self.device}")
+        if bitmap is None:
+            if getattr(self, "bitmap", None) is None:
+                self.bitmap = torch.zeros((self.n, nv.BITMAP_WORDS), dtype=torch.int32, device=self.device)
+            bitmap = self.bitmap
+        self._check_bitmap(bitmap)
+        nxt = None
+        if random_actions:
+            nxt = self.next_actions if next_out is None else next_out
+            if actions.dtype == torch.int32 and nxt.dtype == torch.int64:
+                nxt = nxt.view(torch.int32)[: self.n]
+            if nxt.data_ptr() == actions.data_ptr():
+                raise ValueError("next_out must not alias actions (the kernel reads one while writing the other)")
+        self.step_index += 1
+        nv.check(self._L.kz_step_compact(self.state.data_ptr(), self.n, self.hist_cap, actions.data_ptr(),
+                                         int(actions.dtype == torch.int64), bitmap.data_ptr(), self.reward.data_ptr(),
+                                         self.done.data_ptr(), self.reason.data_ptr(), self.winner.data_ptr(),
+                                         self.ep_len.data_ptr(), self.legal_count.data_ptr(),
+                                         nxt.data_ptr() if nxt is not None else None, self.seed, self.step_index,
+                                         self.env_offset, int(self.auto_reset), self._sp()), "kz_step_compact")
+        return {"bitmap": bitmap, "reward": self.reward, "done": self.done, "reason": self.reason,
+                "winner": self.winner, "ep_len": self.ep_len, "legal_count": self.legal_count}
+
+    def expand(self, bitmap: Optional[torch.Tensor] = None, obs: Optional[torch.Tensor] = None,
+               mask: Optional[torch.Tensor] = None):
+        """Second half of the split pipeline (kz_expand): mask and observation rows of the current positions from the
+        state and the bitmap ``step_compact`` left."""
+        bitmap = self.bitmap if bitmap is None else bitmap
+        self._check_bitmap(bitmap)
+        obs = self.obs if obs is None else obs
+        mask = self.mask if mask is None else mask
+        op, os_ = self._obs_args(obs)
+        mp, ms = self._mask_args(mask)
+        nv.check(self._L.kz_expand(self.state.data_ptr(), self.n, self.hist_cap, bitmap.data_ptr(), op, os_, mp, ms,
+                                   self._sp()), "kz_expand")
+        return obs, mask
+
+    def _check_bitmap(self, bitmap: torch.Tensor) -> None:
+        if (bitmap.device != self.device or bitmap.dtype != torch.int32 or not bitmap.is_contiguous()
+                or tuple(bitmap.shape) != (self.n, nv.BITMAP_WORDS)):
+            raise ValueError(f"bitmap: expected a contiguous int32 [{self.n}, {nv.BITMAP_WORDS}] tensor on {self.device}")
+
     def load_positions(self, boards, hands, side, move_count, max_moves=None, eval_termination: bool = True):
         """ShogiGame.from_sfen for every env from already-parsed arrays (numpy or torch)."""
         d = self.device
