@@ -82,3 +82,33 @@ def test_output_storage_validation_rejects_short_or_misshapen_rows():
                 torch.zeros((4, 9, 9, 46)).permute(0, 3, 1, 2), torch.zeros((46, 9, 9))):
         with pytest.raises(ValueError):
             rows(bad)
+
+
+def test_invalid_arguments_are_rejected_before_any_device_work():
+    """Every entry point returns KZ_E_ARG (-1) -- or KZ_E_NOT_INIT (-3) where the tables come first -- for null
+    pointers and out-of-range sizes, without touching the device (so this runs without a GPU)."""
+    L = nv.lib()
+    z = None
+    bad = (-1, -3)
+    assert L.kz_reset(z, 4, 500, z, 500, z) in bad
+    assert L.kz_load_positions(z, 4, 500, z, z, z, z, z, z) in bad
+    assert L.kz_export_positions(z, 4, 500, z, z, z, z) in bad
+    assert L.kz_refresh(z, 4, 500, z, 0, z, 0, z, z, 1, 0, 0, 0, 0, z, z) in bad
+    assert L.kz_step(z, 4, 500, z, 1, z, 0, z, 0, z, z, z, z, z, z, z, 0, 0, 0, 1, z) == -1
+    assert L.kz_step_compact(z, 4, 500, z, 1, z, z, z, z, z, z, z, z, 0, 0, 0, 1, z) == -1
+    assert L.kz_expand(z, 4, 500, z, z, 0, z, 0, z) == -1
+    assert L.kz_legal_mask(z, 4, 500, z, 0, z, z) == -1
+    assert L.kz_observe(z, 4, 500, z, 0, z) == -1
+    assert L.kz_piece_targets(z, 4, 500, z, z, z) in bad
+    assert L.kz_errors(z, 4, 500, z, 0, z) in bad
+    assert L.kz_sample_masked(z, 0, 13527, z, 13527, 4, 0, 0, z, 1, z, z, 0, z) == -1
+    assert L.kz_gae(z, z, z, z, 8, 4, 0.99, 0.94, z, z, z) == -1
+    assert L.kz_gae_exact(z, z, z, z, 8, 4, 0.99, 0.94, z, z, z) == -1
+    assert L.kz_eval_masked_fwd(z, 0, 13527, z, 13527, z, z, 4, z, z, z, z) == -1
+    assert L.kz_eval_masked_bwd(z, 0, 13527, z, 13527, z, z, 4, z, z, z, z, 13536, z) == -1
+    assert L.kz_eval_masked_bwd_bias(z, 0, 13527, z, 13527, z, z, 4, z, z, z, z, 13536, z, z) == -1
+    assert L.kz_ppo_loss(z, z, z, z, z, z, 4, 0.2, 0.5, 0.01, 1.0, z, z, z, z, z) == -1
+    assert L.kz_obs_conv_fwd(z, z, z, z, 16, 4, 1, z, z) == -1
+    assert L.kz_obs_conv_wgrad(z, z, z, z, 1, 16, 4, z, 1, z, z, z) == -1
+    assert L.kz_adam_clip_step(0, z, z, z, z, z, z, 3e-4, 0.9, 0.999, 1e-8, 0.0, 0.5, z, 0, z, z) == -1
+    assert L.kz_obs_conv_wgrad_ctas(0) <= 0 or L.kz_obs_conv_wgrad_ctas(1) >= 1
