@@ -49,6 +49,34 @@ def timed(label, fn, envs, streams):
     print(f"{label:58s}: {e0.elapsed_time(e1) / K:.4f} ms per {N} env steps")
 
 
+import os
+if os.environ.get("QUICK"):
+    # halves alone, then the overlapped pair: one short call
+    PRE, K = 64, 24
+    one = make(N, 0)
+    for _ in range(PRE):
+        fused(one)
+
+    def compact_only(e):
+        env, act, i = e
+        env.step_compact(act[i[0] & 1], random_actions=True, next_out=act[(i[0] + 1) & 1]); i[0] += 1
+
+    def expand_only(e):
+        e[0].expand()
+
+    cur = [torch.cuda.current_stream()]
+    timed("compact alone, one batch", compact_only, [one], cur)
+    timed("expand alone, one batch", expand_only, [one], cur)
+    del one
+    two = [make(N // 2, 0), make(N // 2, N // 2)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for _ in range(PRE):
+        for e in two:
+            fused(e)
+    torch.cuda.synchronize()
+    timed("(c) split, two groups on two streams", split, two, streams)
+    sys.exit(0)
+
 one = make(N, 0)
 for _ in range(PRE):
     fused(one)

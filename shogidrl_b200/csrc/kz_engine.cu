@@ -1153,6 +1153,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
 #ifndef KZ_EXPAND_CTAS_PER_SM
 #define KZ_EXPAND_CTAS_PER_SM 1
 #endif
+#ifndef KZ_EXPAND_PRELOAD
+#define KZ_EXPAND_PRELOAD 0
+#endif
 #ifndef KZ_COMPACT_CTAS_PER_SM
 #define KZ_COMPACT_CTAS_PER_SM 2  // leaves registers for one expander CTA per SM beside the generating CTAs
 #endif
@@ -1175,9 +1178,20 @@ __global__ void __launch_bounds__(256) kz_expand_kernel(const uint8_t* __restric
       uint8_t* mrow = mask + (size_t)g * mask_stride;
       if (mask_vec) {
         uint4* m4 = reinterpret_cast<uint4*>(mrow);
+#if KZ_EXPAND_PRELOAD
+        uint32_t wreg[27];  // all of this lane's bitmap words in flight at once (the loop below is then pure ALU + stores)
+#pragma unroll
+        for (int k = 0; k < 27; k++) wreg[k] = lane + 32 * k < 846 ? __ldg(bm + ((lane + 32 * k) >> 1)) : 0u;
+#pragma unroll
+        for (int k = 0; k < 27; k++) {
+          const int q = lane + 32 * k;
+          if (q >= 846) break;
+          const uint32_t w = wreg[k];
+#else
 #pragma unroll 4
         for (int q = lane; q < 846; q += 32) {  // chunk q = bits [16q, 16q + 16): every chunk is written, no zero fill
           const uint32_t w = __ldg(bm + (q >> 1));
+#endif
           const uint4 v = expand((q & 1) ? (w >> 16) : (w & 0xFFFF));
           if (q < 845 || mask_stride >= 13536) m4[q] = v;
           else {  // last 7 bytes of an exactly-13,527-byte aligned row
