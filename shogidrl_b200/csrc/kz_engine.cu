@@ -1156,6 +1156,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
 #ifndef KZ_EXPAND_PRELOAD
 #define KZ_EXPAND_PRELOAD 0
 #endif
+#ifndef KZ_EXPAND_SPARSE
+#define KZ_EXPAND_SPARSE 0
+#endif
 #ifndef KZ_COMPACT_CTAS_PER_SM
 #define KZ_COMPACT_CTAS_PER_SM 2  // leaves registers for one expander CTA per SM beside the generating CTAs
 #endif
@@ -1178,6 +1181,25 @@ __global__ void __launch_bounds__(256) kz_expand_kernel(const uint8_t* __restric
       uint8_t* mrow = mask + (size_t)g * mask_stride;
       if (mask_vec) {
         uint4* m4 = reinterpret_cast<uint4*>(mrow);
+#if KZ_EXPAND_SPARSE
+        // (untested variant for the next round) the fused kernel's recipe: zero-fill the padded row with 256-bit stores,
+        // then expand only the chunks that hold a legal action (about a fifth of them)
+        if (mask_stride >= 13536 && (((uintptr_t)mrow) & 31) == 0) {
+          uint32_t wreg[27];
+#pragma unroll
+          for (int k = 0; k < 27; k++) wreg[k] = lane + 32 * k < 846 ? __ldg(bm + ((lane + 32 * k) >> 1)) : 0u;
+#pragma unroll 1
+          for (int q = lane; q < 423; q += 32) st_zero256(mrow + 32 * q);
+          __syncwarp();  // the overwrites follow the zero fill in program order
+#pragma unroll
+          for (int k = 0; k < 27; k++) {
+            const int q = lane + 32 * k;
+            const uint32_t half = (q & 1) ? (wreg[k] >> 16) : (wreg[k] & 0xFFFF);
+            if (q < 846 && half) m4[q] = expand(half);
+          }
+        } else
+#endif
+        {
 #if KZ_EXPAND_PRELOAD
         uint32_t wreg[27];  // all of this lane's bitmap words in flight at once (the loop below is then pure ALU + stores)
 #pragma unroll
@@ -1198,6 +1220,7 @@ __global__ void __launch_bounds__(256) kz_expand_kernel(const uint8_t* __restric
             const uint32_t parts[2] = {v.x, v.y};
             for (int b = 0; b < 7; b++) mrow[13520 + b] = (uint8_t)(parts[b >> 2] >> (8 * (b & 3)));
           }
+        }
         }
       } else {
         for (int i = lane; i < KZ_NUM_ACTIONS; i += 32) mrow[i] = (uint8_t)((__ldg(bm + (i >> 5)) >> (i & 31)) & 1);
