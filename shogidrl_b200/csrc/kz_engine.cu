@@ -973,7 +973,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
       uint8_t* mrow = P.mask + (size_t)g * P.mask_stride;
       if (P.mask_vec) {
         // 16-byte chunk q of the row = bits [16q, 16q+16) of the bitmap; a from-square owns chunks 10f..10f+9.
-        // Pass 1 zero-fills the 810 board-move chunks with plain 128-bit stores; pass 2 expands only the chunks
+        // Pass 1 zero-fills the 810 board-move chunks (256-bit stores on 32-byte aligned rows); pass 2 expands only the chunks
         // of from-squares that have a legal move (3 squares x 10 chunks per warp round) and the 36 drop chunks.
         uint4* m4 = reinterpret_cast<uint4*>(mrow);
         if (!KZ_FILL_AFTER_COMPACT && !(KZ_BULK_ZERO & 1)) fill_mask_zero();
