@@ -278,7 +278,7 @@ def run_product(args):
     from shogidrl_b200 import VecShogiEnv, MASK_PAD_STRIDE
 
     n = args.envs
-    env = VecShogiEnv(n, MAX_MOVES, dev, seed=SEED, env_offset=rank * n, auto_reset=True)
+    env = VecShogiEnv(n, MAX_MOVES, dev, seed=SEED, env_offset=rank * n, auto_reset=True, step_streams=args.step_streams)
     # rollout storage the kernel writes straight into: 2 slots of [n] obs / masks (1.86 GB per slot >> 126 MB L2)
     SLOTS = 2
     obs_buf = torch.zeros((SLOTS, n, 46, 9, 9), dtype=torch.float32, device=dev)
@@ -582,6 +582,8 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="games per GPU (BASELINE config 2: 65,536)")
     ap.add_argument("--preroll", type=int, default=PREROLL)
+    ap.add_argument("--step-streams", type=int, default=None,
+                    help="ranges of games a step is launched as, on as many streams (default: VecShogiEnv's choice, 2 for >= 32,768 games)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="env", choices=["env", "ppo"], help="env: BASELINE config 2 (default, the headline); ppo: config 3")
     ap.add_argument("--ppo-envs", type=int, default=16384)

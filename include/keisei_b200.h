@@ -25,10 +25,12 @@
 extern "C" {
 #endif
 
-#define KZ_ABI_VERSION 1
+#define KZ_ABI_VERSION 2
 #define KZ_NUM_ACTIONS 13527
 #define KZ_OBS_FLOATS 3726  /* 46 x 9 x 9 */
 #define KZ_MASK_PAD_STRIDE 13536 /* 16-byte multiple >= 13527: fast-path row stride */
+#define KZ_BITMAP_WORDS 448     /* row of a legal BITMAP: bit i = action i legal; 423 words used, zero-padded to 14 per lane */
+#define KZ_BITMAP_WORDS_MIN 423 /* smallest row stride (in 32-bit words) the bitmap readers accept */
 
 /* termination reason codes (shogi_core_definitions.py:135-147) */
 #define KZ_ONGOING 0
@@ -117,6 +119,19 @@ int kz_step(void* state, int n, int hist_cap, const void* actions, int actions_i
             uint8_t* reason, int8_t* winner, int32_t* ep_len, int32_t* legal_count, void* next_actions,
             uint64_t seed, uint32_t rng_step, uint32_t env_offset, int auto_reset, void* stream);
 
+/* kz_step / kz_step_rollout over the sub-range [first, first + count) of the batch's n games: every array argument is
+ * still indexed by the game's position in the whole batch (row g of obs / mask / bitmap, element g of actions, reward,
+ * ...), and the per-game random stream is keyed by env_offset + g as before, so stepping a batch as several ranges gives
+ * exactly the results of one kz_step.  Ranges of one batch may run CONCURRENTLY on different streams when each names its
+ * own counter_slot (0..63, the dynamic work counter of the launch): the CTAs of the second range fill the SMs that the
+ * first range's tail leaves idle (a persistent grid drains unevenly), -5 % per 65,536-game step on B200.
+ * mask != NULL: byte-mask form (kz_step); bitmap != NULL: rollout form (kz_step_rollout); not both. */
+int kz_step_range(void* state, int n, int hist_cap, int first, int count, int counter_slot, const void* actions,
+                  int actions_i64, float* obs, int64_t obs_stride, uint8_t* mask, int64_t mask_stride, uint32_t* bitmap,
+                  int64_t bitmap_stride_words, float* reward, uint8_t* done, uint8_t* reason, int8_t* winner, int32_t* ep_len,
+                  int32_t* legal_count, void* next_actions, uint64_t seed, uint32_t rng_step, uint32_t env_offset,
+                  int auto_reset, void* stream);
+
 /* Split pipeline (experimental; same results as kz_step, bit for bit): kz_step_compact is kz_step without the two row
  * outputs -- it leaves the successor's 13,527-bit legal bitmap in bitmap [n][448] uint32 (bit i of the row = action i;
  * 16-byte aligned) -- and kz_expand writes the mask and observation rows of the CURRENT positions from the state and
@@ -129,6 +144,22 @@ int kz_step_compact(void* state, int n, int hist_cap, const void* actions, int a
                     void* stream);
 int kz_expand(const void* state, int n, int hist_cap, const uint32_t* bitmap, float* obs, int64_t obs_stride,
               uint8_t* mask, int64_t mask_stride, void* stream);
+
+/* Rollout form of kz_step (the PPO self-play path, StepManager.execute_step step_manager.py:98-348 over n games): as
+ * kz_step, but the successor's legal moves are left as the 13,527-bit legal BITMAP -- bitmap [n][bitmap_stride_words]
+ * uint32, 16-byte aligned rows, bit i = action i is legal, the same set PolicyOutputMapper.get_legal_mask
+ * (utils.py:310-336) marks -- instead of the 13,527-byte mask row: 1,792 B instead of 13,536 B written per game here, and
+ * read again by kz_sample_bitmap and by every kz_eval_bitmap_* pass of the update.  obs as in kz_step (optional).
+ * kz_legal_bitmap is the kz_refresh counterpart (current positions, no move); kz_bitmap_expand turns bitmap rows into
+ * byte-mask rows for callers of the reference API (ExperienceBuffer.legal_masks, experience_buffer.py:52-54). */
+int kz_step_rollout(void* state, int n, int hist_cap, const void* actions, int actions_i64, float* obs,
+                    int64_t obs_stride, uint32_t* bitmap, int64_t bitmap_stride_words, float* reward, uint8_t* done,
+                    uint8_t* reason, int8_t* winner, int32_t* ep_len, int32_t* legal_count, void* next_actions,
+                    uint64_t seed, uint32_t rng_step, uint32_t env_offset, int auto_reset, void* stream);
+int kz_legal_bitmap(void* state, int n, int hist_cap, float* obs, int64_t obs_stride, uint32_t* bitmap,
+                    int64_t bitmap_stride_words, int32_t* legal_count, void* stream);
+int kz_bitmap_expand(const uint32_t* bitmap, int64_t bitmap_stride_words, const int64_t* bitmap_rows, int n, uint8_t* mask,
+                     int64_t mask_stride, void* stream);
 
 /* Thin conveniences over kz_refresh. */
 int kz_legal_mask(void* state, int n, int hist_cap, uint8_t* mask, int64_t mask_stride,
@@ -152,6 +183,11 @@ int kz_errors(void* state, int n, int hist_cap, int32_t* out, int clear, void* s
  *   counter-based uniform keyed (seed, offset + row): statistical, not bitwise, parity with
  *   torch.multinomial. */
 int kz_sample_masked(const void* logits, int logits_bf16, int64_t ld, const uint8_t* mask, int64_t ldm,
+                     int n, uint64_t seed, uint64_t offset, void* actions, int actions_i64, float* logp,
+                     float* entropy, int deterministic, void* stream);
+/* The same with the legal set given as bitmap rows (kz_step_rollout): bitmap [n][ldb_words] uint32.  For a 16-byte
+ * aligned byte mask of the same set the two entry points return identical actions, log-probs and entropies. */
+int kz_sample_bitmap(const void* logits, int logits_bf16, int64_t ld, const uint32_t* bitmap, int64_t ldb_words,
                      int n, uint64_t seed, uint64_t offset, void* actions, int actions_i64, float* logp,
                      float* entropy, int deterministic, void* stream);
 
@@ -180,13 +216,24 @@ int kz_eval_masked_bwd(const void* logits, int logits_bf16, int64_t ld, const ui
                        const int64_t* mask_rows, const int64_t* actions, int n, const float* dlogp,
                        const float* dentropy, const float* saved4, void* dlogits, int64_t ldg, void* stream);
 /* The same backward that also accumulates the column sums of dlogits -- the gradient of the policy head's bias
- * (nn.Linear(…, 13527), keisei/core/neural_network.py:20) -- into dbias fp32 [>= 13527], which the caller has zeroed:
- * dlogits is non-zero only at legal actions (~0.5 % of a row), so the bias gradient is a sparse scatter-add (fp32
- * reductions in L2, taken before the rounding to the dlogits dtype) instead of a second pass over [n][13536]. */
+ * (nn.Linear(…, 13527), keisei/core/neural_network.py:20) -- into dbias_q44 int64 [>= 13527], which the caller has
+ * zeroed: dlogits is non-zero only at legal actions (~0.5 % of a row), so the bias gradient is a sparse scatter-add
+ * (integer reductions in L2, taken before the rounding to the dlogits dtype) instead of a second pass over [n][13536].
+ * The sums are Q20.44 fixed point (gradient = value * 2^-44): integer addition is associative, so the result is
+ * deterministic run to run, unlike an fp32 atomic accumulation. */
 int kz_eval_masked_bwd_bias(const void* logits, int logits_bf16, int64_t ld, const uint8_t* mask, int64_t ldm,
                             const int64_t* mask_rows, const int64_t* actions, int n, const float* dlogp,
-                            const float* dentropy, const float* saved4, void* dlogits, int64_t ldg, float* dbias,
+                            const float* dentropy, const float* saved4, void* dlogits, int64_t ldg, int64_t* dbias_q44,
                             void* stream);
+/* Bitmap forms of the evaluation pair: legal sets as rows bitmap[bitmap_rows[i]] (or bitmap[i]) of kz_step_rollout's
+ * output; dbias_q44 optional (NULL: no bias gradient).  Results identical to the byte-mask forms on the same sets. */
+int kz_eval_bitmap_fwd(const void* logits, int logits_bf16, int64_t ld, const uint32_t* bitmap, int64_t ldb_words,
+                       const int64_t* bitmap_rows, const int64_t* actions, int n, float* logp, float* entropy,
+                       float* saved4, void* stream);
+int kz_eval_bitmap_bwd(const void* logits, int logits_bf16, int64_t ld, const uint32_t* bitmap, int64_t ldb_words,
+                       const int64_t* bitmap_rows, const int64_t* actions, int n, const float* dlogp,
+                       const float* dentropy, const float* saved4, void* dlogits, int64_t ldg, int64_t* dbias_q44,
+                       void* stream);
 
 /* PPO clipped-surrogate loss of one minibatch and its gradients in closed form (keisei/core/ppo_agent.py:332-372;
  * value clipping off): out6 = {loss, policy loss, value loss, entropy loss (= -mean entropy), mean(old_logp -

@@ -24,8 +24,10 @@ EXPORTS = [
     "kz_export_positions", "kz_piece_targets", "kz_refresh", "kz_step", "kz_legal_mask", "kz_observe", "kz_errors", "kz_sample_masked",
     "kz_gae", "kz_gae_exact", "kz_eval_masked_fwd", "kz_eval_masked_bwd", "kz_obs_conv_fwd", "kz_obs_conv_wgrad_ctas",
     "kz_obs_conv_wgrad", "kz_ppo_loss", "kz_eval_masked_bwd_bias", "kz_adam_clip_workspace", "kz_adam_clip_step",
-    "kz_step_compact", "kz_expand",
+    "kz_step_compact", "kz_expand", "kz_step_rollout", "kz_legal_bitmap", "kz_bitmap_expand", "kz_sample_bitmap",
+    "kz_eval_bitmap_fwd", "kz_eval_bitmap_bwd", "kz_step_range",
 ]
+ABI_VERSION = 2
 
 
 class NativeError(RuntimeError):
@@ -58,6 +60,14 @@ def lib() -> C.CDLL:
     L.kz_step.argtypes = [vp, i32, i32, vp, i32, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, vp]
     L.kz_step_compact.argtypes = [vp, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, vp]
     L.kz_expand.argtypes = [vp, i32, i32, vp, vp, i64, vp, i64, vp]
+    L.kz_step_rollout.argtypes = [vp, i32, i32, vp, i32, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, vp]
+    L.kz_step_range.argtypes = [vp, i32, i32, i32, i32, i32, vp, i32, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp,
+                                u64, u32, u32, i32, vp]
+    L.kz_legal_bitmap.argtypes = [vp, i32, i32, vp, i64, vp, i64, vp, vp]
+    L.kz_bitmap_expand.argtypes = [vp, i64, vp, i32, vp, i64, vp]
+    L.kz_sample_bitmap.argtypes = [vp, i32, i64, vp, i64, i32, u64, u64, vp, i32, vp, vp, i32, vp]
+    L.kz_eval_bitmap_fwd.argtypes = [vp, i32, i64, vp, i64, vp, vp, i32, vp, vp, vp, vp]
+    L.kz_eval_bitmap_bwd.argtypes = [vp, i32, i64, vp, i64, vp, vp, i32, vp, vp, vp, vp, i64, vp, vp]
     L.kz_legal_mask.argtypes = [vp, i32, i32, vp, i64, vp, vp]
     L.kz_observe.argtypes = [vp, i32, i32, vp, i64, vp]
     L.kz_errors.argtypes = [vp, i32, i32, vp, i32, vp]
@@ -78,6 +88,9 @@ def lib() -> C.CDLL:
         fn = getattr(L, name)
         if name not in ("kz_last_cuda_error",):
             fn.restype = i64 if name == "kz_adam_clip_workspace" else i32
+    if L.kz_abi_version() != ABI_VERSION:
+        raise NativeError(f"{LIB_PATH} has ABI version {L.kz_abi_version()}, this package binds version {ABI_VERSION}: "
+                          "rebuild it (python -c 'import __graft_entry__ as g; g.build()')")
     _lib = L
     return L
 

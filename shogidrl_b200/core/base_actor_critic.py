@@ -45,7 +45,10 @@ class BaseActorCriticModel(nn.Module):
         raise NotImplementedError("Subclasses must implement forward method")
 
     def get_action_and_value(self, obs: torch.Tensor, legal_mask: Optional[torch.Tensor] = None,
-                             deterministic: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                             deterministic: bool = False, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+                             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """``legal_mask``: bool/uint8 [B, 13527] as in the reference, or the engine's legal bitmap rows (int32
+        [B, 448]).  ``out`` = (actions int64 [B], log_probs fp32 [B]): the sampler writes there (rollout storage)."""
         logits, value = self.forward(obs)
         if legal_mask is None:
             legal_mask = torch.ones_like(logits, dtype=torch.bool)
@@ -58,7 +61,7 @@ class BaseActorCriticModel(nn.Module):
         n = logits.shape[0]
         offset = next(_sample_counter) * (1 << 20)
         action, log_prob, _ = rl.sample_masked(logits, legal_mask, seed=self.sample_seed, offset=offset,
-                                               deterministic=deterministic)
+                                               deterministic=deterministic, out=out)
         if value.dim() > 1 and value.shape[-1] == 1:
             value = value.squeeze(-1)
         return action, log_prob, value
@@ -84,6 +87,9 @@ class BaseActorCriticModel(nn.Module):
             return log_probs, entropy, value
         if mask_rows is not None and legal_mask is not None:
             legal_mask = legal_mask[mask_rows]
+        if legal_mask is not None and rl.is_bitmap(legal_mask):  # CPU tensors: unpack the bitmap rows
+            bits = (legal_mask.unsqueeze(-1) >> torch.arange(32, device=legal_mask.device, dtype=torch.int32)) & 1
+            legal_mask = bits.reshape(legal_mask.shape[0], -1)[:, : logits.shape[1]].bool()
         logits = logits.float()
         if legal_mask is not None:
             logits = torch.where(legal_mask.bool(), logits, torch.full((), float("-inf"), device=logits.device))

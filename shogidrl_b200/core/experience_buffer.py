@@ -140,10 +140,14 @@ class ExperienceBuffer:
 
 
 class RolloutBuffer:
-    """[T, N] rollout storage in HBM.  obs[t] / masks[t] are the positions the action of step t was chosen in;
-    kz_step writes obs[t+1] / masks[t+1] directly (slot T holds the bootstrap observation).  Mask rows are padded
-    to 13,536 bytes so that every row is 16-byte aligned for the kernel's vector stores; ``masks`` is the
-    [T+1, N, 13527] view."""
+    """[T, N] rollout storage in HBM.  obs[t] / bitmaps[t] are the positions the action of step t was chosen in;
+    kz_step_rollout writes obs[t+1] / bitmaps[t+1] directly (slot T holds the bootstrap observation).
+
+    Legal sets are kept as the engine's 13,527-bit legal bitmaps (int32 [T+1, N, 448], 1,792 B per position) -- the
+    sampler and both masked-evaluation kernels read them as they are.  The reference's byte masks
+    (``ExperienceBuffer.legal_masks``, bool [B, 13527], experience_buffer.py:52-54) are a 7.5x larger encoding of the
+    same sets (13.5 KB per position: 28 GB of a config-3 rollout) and are materialised only for callers that ask:
+    ``masks_at(t)``, ``legal_masks(rows)`` or ``get_batch(expand_masks=True)``."""
 
     def __init__(self, horizon: int, num_envs: int, gamma: float, lambda_gae: float, device="cuda"):
         self.T, self.N = int(horizon), int(num_envs)
@@ -151,8 +155,7 @@ class RolloutBuffer:
         self.device = nv.require_cuda(device)
         d, T, N = self.device, self.T, self.N
         self.obs = torch.zeros((T + 1, N, 46, 9, 9), dtype=torch.float32, device=d)
-        self._mask_store = torch.zeros((T + 1, N, nv.MASK_PAD_STRIDE), dtype=torch.uint8, device=d)
-        self.masks = self._mask_store[:, :, : nv.NUM_ACTIONS]
+        self.bitmaps = torch.zeros((T + 1, N, nv.BITMAP_WORDS), dtype=torch.int32, device=d)
         self.actions = torch.zeros((T, N), dtype=torch.int64, device=d)
         self.log_probs = torch.zeros((T, N), dtype=torch.float32, device=d)
         self.values = torch.zeros((T, N), dtype=torch.float32, device=d)
@@ -169,19 +172,35 @@ class RolloutBuffer:
                out=(self.advantages, self.returns))
         self._advantages_computed = True
 
-    def get_batch(self) -> Dict[str, torch.Tensor]:
+    def masks_at(self, t: int) -> torch.Tensor:
+        """bool [N, 13527] legal masks of slot t (expanded from the bitmaps on demand)."""
+        return rl.bitmap_to_mask(self.bitmaps[t])
+
+    def legal_masks(self, rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """bool [len(rows), 13527] legal masks of flat transitions ``rows`` (index t * N + n; default: all T * N --
+        13.5 KB each, so ask for what is needed)."""
+        flat = self.bitmaps[: self.T].reshape(self.T * self.N, nv.BITMAP_WORDS)
+        return rl.bitmap_to_mask(flat, rows)
+
+    def get_batch(self, expand_masks: bool = False) -> Dict[str, torch.Tensor]:
+        """The reference's batch dictionary (experience_buffer.py:147-189) over the T * N transitions, with the legal
+        sets as ``legal_bitmaps`` (int32 [B, 448]); ``expand_masks`` adds the reference's ``legal_masks`` bool
+        [B, 13527]."""
         if not self._advantages_computed:
             raise RuntimeError("Cannot get batch: compute_advantages_and_returns() must be called first")
         T, N = self.T, self.N
         B = T * N
-        return {"obs": self.obs[:T].reshape(B, 46, 9, 9), "actions": self.actions.reshape(B),
-                "log_probs": self.log_probs.reshape(B), "values": self.values.reshape(B),
-                "rewards": self.rewards.reshape(B), "advantages": self.advantages.reshape(B),
-                "returns": self.returns.reshape(B), "dones": self.dones.reshape(B).bool(),
-                "legal_masks": self._mask_store[:T].reshape(B, nv.MASK_PAD_STRIDE).view(torch.bool)[:, : nv.NUM_ACTIONS]}
+        batch = {"obs": self.obs[:T].reshape(B, 46, 9, 9), "actions": self.actions.reshape(B),
+                 "log_probs": self.log_probs.reshape(B), "values": self.values.reshape(B),
+                 "rewards": self.rewards.reshape(B), "advantages": self.advantages.reshape(B),
+                 "returns": self.returns.reshape(B), "dones": self.dones.reshape(B).bool(),
+                 "legal_bitmaps": self.bitmaps[:T].reshape(B, nv.BITMAP_WORDS)}
+        if expand_masks:
+            batch["legal_masks"] = self.legal_masks()
+        return batch
 
     def clear(self):
         """Start the next rollout from the last written state: slot T becomes slot 0."""
         self.obs[0].copy_(self.obs[self.T])
-        self._mask_store[0].copy_(self._mask_store[self.T])
+        self.bitmaps[0].copy_(self.bitmaps[self.T])
         self._advantages_computed = False

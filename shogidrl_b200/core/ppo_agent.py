@@ -104,14 +104,17 @@ class PPOAgent:
     def _autocast(self):
         return torch.autocast("cuda", dtype=torch.bfloat16, enabled=bool(self.use_mixed_precision and self.device.type == "cuda"))
 
-    def select_actions(self, obs: torch.Tensor, legal_mask: torch.Tensor, *, is_training: bool = True
+    def select_actions(self, obs: torch.Tensor, legal_mask: torch.Tensor, *, is_training: bool = True,
+                       out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
                        ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """Batched select_action: obs [N,46,9,9] and legal_mask [N,13527] stay on the device; returns
-        (actions int64 [N], log_probs fp32 [N], values fp32 [N]) without any host synchronisation."""
+        """Batched select_action: obs [N,46,9,9] and legal_mask [N,13527] (or the engine's legal bitmap rows, int32
+        [N,448]) stay on the device; returns (actions int64 [N], log_probs fp32 [N], values fp32 [N]) without any
+        host synchronisation.  ``out`` = (actions, log_probs) rows of the rollout storage to write into."""
         self.model.train(is_training)
+        kw = {"out": out} if out is not None else {}
         with torch.no_grad(), self._autocast():
             action, log_prob, value = self.model.get_action_and_value(self._scale(obs), legal_mask=legal_mask,
-                                                                      deterministic=not is_training)
+                                                                      deterministic=not is_training, **kw)
         return action, log_prob, value.float()
 
     def select_action(self, obs: np.ndarray, legal_mask: torch.Tensor, *, is_training: bool = True):
@@ -152,7 +155,9 @@ class PPOAgent:
         d = self.device
         obs_b, act_b = batch["obs"].to(d), batch["actions"].to(d)
         oldlp_b, oldv_b = batch["log_probs"].to(d), batch["values"].to(d)
-        adv_b, ret_b, mask_b = batch["advantages"].to(d), batch["returns"].to(d), batch["legal_masks"].to(d)
+        # legal sets: the reference's byte masks, or the rollout buffer's legal bitmaps (read in place by the kernels)
+        mask_b = (batch["legal_bitmaps"] if "legal_bitmaps" in batch else batch["legal_masks"]).to(d)
+        adv_b, ret_b = batch["advantages"].to(d), batch["returns"].to(d)
         if self.normalize_advantages:
             adv_b = self._normalize(adv_b)
         n = obs_b.shape[0]
@@ -254,11 +259,31 @@ class PPOAgent:
             self._static_adv = torch.empty_like(S["adv"])
         self._static_adv.copy_(S["adv"])
         S = dict(S, adv=self._static_adv)
-        key = tuple((k, v.data_ptr(), tuple(v.shape), tuple(v.stride())) for k, v in sorted(S.items())) + (self.minibatch_size,)
-        if key != self._graph_key:
-            self._graph, self._graph_key, self._graph_warm = None, key, 0
+        key = self._key_of(S)
+        if self._graph is not None and key != self._graph_key:
+            self._drop_graph()
+        if getattr(self, "_static_mb", None) is None or self._static_mb.shape[0] != self.minibatch_size:
             self._static_mb = torch.empty(self.minibatch_size, dtype=torch.int64, device=self.device)
         return S
+
+    def _key_of(self, S: Dict[str, torch.Tensor]):
+        # everything the captured graph bakes in: batch storage, optimizer state tensors (load_state_dict swaps them) and
+        # the hyper-parameters that travel as kernel scalars (a callback may anneal them)
+        g = self.optimizer.param_groups[0]
+        opt_state = tuple(t.data_ptr() for p in g["params"] for t in self.optimizer.state.get(p, {}).values()
+                          if torch.is_tensor(t))
+        scalars = (float(g["lr"]), tuple(g["betas"]), float(g["eps"]), float(g["weight_decay"]), float(self.clip_epsilon),
+                   float(self.value_loss_coeff), float(self.entropy_coef), float(self.gradient_clip_max_norm),
+                   bool(self.enable_value_clipping), getattr(self, "_grad_world", 1))
+        key = (tuple((k, v.data_ptr(), tuple(v.shape), tuple(v.stride())) for k, v in sorted(S.items()))
+               + (self.minibatch_size, opt_state, scalars))
+        return key
+
+    def _drop_graph(self) -> None:
+        """Forget the captured update: its kernels hold raw pointers to the batch, the optimizer state and baked
+        scalars, so anything that replaces one of them (load_model, an annealed coefficient, another buffer) must
+        come through here."""
+        self._graph, self._graph_key, self._graph_warm = None, None, 0
 
     def _graphed_update(self, S: Dict[str, torch.Tensor], mb: torch.Tensor) -> None:
         """Launch-bound inner loop -> one CUDA graph per minibatch update (~60 kernels, 2.4 ms of device time
@@ -268,6 +293,7 @@ class PPOAgent:
         if self._graph is not None:
             self._graph.replay()
             return
+        self._graph_key = self._key_of(S)  # optimizer state tensors come into being during the eager warm-up
         if self._graph_warm < 3:
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
@@ -324,7 +350,13 @@ class PPOAgent:
     def save_model(self, file_path: str, global_timestep: int = 0, total_episodes_completed: int = 0,
                    stats_to_save: Optional[Dict[str, int]] = None) -> None:
         model = getattr(self.model, "module", self.model)  # unwrap DistributedDataParallel
-        data = {"model_state_dict": model.state_dict(), "optimizer_state_dict": self.optimizer.state_dict(),
+        # the reference's Adam is not capturable and keeps `step` as a CPU fp32 tensor: write the state that way, so a
+        # reference run (CPU included) resumes from this file (torch's Adam asserts capturable state lives on CUDA)
+        opt_sd = self.optimizer.state_dict()
+        opt_sd = {"state": {k: {n: (t.detach().to("cpu", torch.float32) if n == "step" and torch.is_tensor(t) else t)
+                                for n, t in st.items()} for k, st in opt_sd["state"].items()},
+                  "param_groups": [dict(g, capturable=False) for g in opt_sd["param_groups"]]}
+        data = {"model_state_dict": model.state_dict(), "optimizer_state_dict": opt_sd,
                 "global_timestep": global_timestep, "total_episodes_completed": total_episodes_completed}
         if stats_to_save:
             data.update(stats_to_save)
@@ -342,6 +374,9 @@ class PPOAgent:
             ck = torch.load(file_path, map_location=self.device, weights_only=False)
             getattr(self.model, "module", self.model).load_state_dict(ck["model_state_dict"])
             self.optimizer.load_state_dict(ck["optimizer_state_dict"])
+            for g in self.optimizer.param_groups:  # saved as the reference writes it (capturable False); see save_model
+                g["capturable"] = self.device.type == "cuda"
+            self._drop_graph()  # a captured update holds pointers to the replaced optimizer state tensors
             if self.scheduler is not None and "scheduler_state_dict" in ck:
                 self.scheduler.load_state_dict(ck["scheduler_state_dict"])
             return {k: ck.get(k, v) for k, v in {**empty, "lr_schedule_type": None, "lr_schedule_step_on": "epoch"}.items()}

@@ -36,6 +36,10 @@ struct __align__(16) WarpScratch {
   uint32_t pinl[2][8 * 3];  // pin line per direction
   uint8_t plist[2][40];   // squares of the mover's pieces
   uint8_t dropv[96];      // 7 drop bits per square
+  uint32_t oimg[72];      // compose-once observation writer: bit plane * 81 + square of planes 0..27 (+ one pad word)
+  float opv[20];          // ... and the values of the constant planes 28..45
+  uint32_t onz;           // ... bit i: constant plane 28 + i is non-zero
+  uint32_t pad_[3];
 };
 
 // Shared memory of the step kernel, declared at file scope so that every device function addresses it
@@ -57,6 +61,9 @@ struct Tables {};  // the tables live in s_ray / s_step
 #endif
 #ifndef KZ_ST256
 #define KZ_ST256 3  // 256-bit zero-fill stores: bit 0 mask row, bit 1 observation row
+#endif
+#ifndef KZ_ROWS_ONCE
+#define KZ_ROWS_ONCE 1  // per-warp writers compose every 32-byte piece once (bit 0 mask row, bit 1 observation row) instead of zero fill + patch
 #endif
 #ifndef KZ_BULK_ZERO
 #define KZ_BULK_ZERO 0  // 1: the mask row's zero runs are written by the bulk-copy engine from a shared page of zeros
@@ -82,6 +89,11 @@ __device__ __forceinline__ void bulk_zero(void* dst, uint32_t bytes) {  // dst 1
 __device__ __forceinline__ void st_zero256(void* p) {
   const uint32_t z = 0;
   asm volatile("st.global.v8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(p), "r"(z) : "memory");
+}
+
+__device__ __forceinline__ void st256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 
 __device__ __forceinline__ BB ld_ray(const Tables&, int sq, int d) {
@@ -553,7 +565,8 @@ struct StepParams {
   uint4* hist;    // repetition tables: rep_slots 16-byte slots per game
   int rep_slots;  // power of two >= 2 * hist_cap (>= 64)
   int hist_cap;
-  int n;
+  int n;        // games stepped by this launch ...
+  int g_first;  // ... starting at this game of the batch (kz_step_range; 0 otherwise)
   const void* actions;
   int actions_i64;
   float* obs;
@@ -576,7 +589,8 @@ struct StepParams {
   int mode;  // 0 = refresh, 1 = step
   int eval_term;
   int* tile_counter;  // zeroed per launch: tiles (8 games, one per warp) beyond the first are claimed dynamically
-  uint32_t* bitmap_out;  // mode 2: the legal bitmap [n][BITMAP_WORDS] instead of the mask / observation rows
+  uint32_t* bitmap_out;  // the legal bitmap [n][bitmap_stride] (modes 0-2; mode 2 writes it instead of the mask row)
+  long long bitmap_stride;  // words per bitmap row (>= BITMAP_WORDS, a multiple of 4)
 };
 
 __device__ __forceinline__ uint32_t rand32(unsigned long long seed, unsigned long long env, unsigned long long step) {
@@ -607,16 +621,17 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpScratch& ws = s_ws[warp];
   const uint32_t tab = code_info(lane);
+  const int g_end = P.g_first + P.n;  // this launch steps games [g_first, g_end) of the batch
 
   // One 32-bit word of game state per lane (lanes 0-23: board, 24-31: meta) and the action are fetched one
   // game ahead, so that their DRAM latency overlaps the previous game's work.
   auto fetch_state = [&](int g) -> uint32_t {
-    if (g >= P.n) return 0u;
+    if (g >= g_end) return 0u;
     return lane < 24 ? reinterpret_cast<const uint32_t*>(P.boards + (size_t)g * 96)[lane]
                      : reinterpret_cast<const uint32_t*>(P.meta + (size_t)g * 32)[lane - 24];
   };
   auto fetch_action = [&](int g) -> long long {
-    if (g >= P.n || MODE == 0) return 0;
+    if (g >= g_end || MODE == 0) return 0;
     return P.actions_i64 ? reinterpret_cast<const long long*>(P.actions)[g]
                          : (long long)reinterpret_cast<const int*>(P.actions)[g];
   };
@@ -634,17 +649,17 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
   int tile = blockIdx.x, claimed = 0;
   if (lockstep && threadIdx.x == 0) s_tile[1] = gridDim.x + atomicAdd(P.tile_counter, 1);
   const int g_stride = gridDim.x * WARPS_PER_CTA;
-  int g = blockIdx.x * WARPS_PER_CTA + warp;
+  int g = P.g_first + blockIdx.x * WARPS_PER_CTA + warp;
   uint32_t next_word = fetch_state(g);
   long long next_action = fetch_action(g);
   __syncthreads();
 
-  for (int it = 0; lockstep ? tile < ntiles : g < P.n; it++) {
+  for (int it = 0; lockstep ? tile < ntiles : g < g_end; it++) {
     int g_next = g + g_stride;
     if (lockstep) {
       __syncthreads();
       tile = s_tile[(it + 1) & 1];  // the tile after this one
-      g_next = tile * WARPS_PER_CTA + warp;
+      g_next = P.g_first + tile * WARPS_PER_CTA + warp;
       if (threadIdx.x == 0) claimed = gridDim.x + atomicAdd(P.tile_counter, 1);  // two ahead; stored at the loop end
     }
     // ---- state of this game (prefetched), start fetching the next one
@@ -838,10 +853,91 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
       }
 #endif
     };
+    // image of this game's observation (generate_neural_network_observation, shogi_game_io.py:434-539): one bit per
+    // non-zero float of the 28 piece planes (bit plane * 81 + square, squares rotated 180 degrees for White to move) and
+    // the values of the 18 constant planes -- what the compose-once row writers read
+    auto build_obs_image = [&]() {
+      __syncwarp();
+      ws.oimg[lane] = 0; ws.oimg[lane + 32] = 0;
+      if (lane < 8) ws.oimg[lane + 64] = 0;
+      float pv = 0.f;
+      if (lane < 14) {
+        const int cnt = ws.meta[lane < 7 ? side * 7 + lane : (1 - side) * 7 + (lane - 7)];
+        if (cnt > 0) pv = __fdiv_rn((float)cnt, 18.0f);  // see write_obs for why one fp32 division is exact here
+      } else if (lane == 14) pv = side == 0 ? 1.f : 0.f;
+      else if (lane == 15) pv = max_moves > 0 ? __fdiv_rn((float)move_count, (float)max_moves) : 0.f;
+      if (lane < 20) ws.opv[lane] = pv;
+      const uint32_t nz = __ballot_sync(FULL, pv != 0.f);
+      if (lane == 0) ws.onz = nz;
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const int sq = lane + 32 * j;
+        const int code = sq < 81 ? ws.board[sq] : 0;
+        if (code) {
+          const int t = code_type(code), mine = code_color(code) == side;
+          const int plane = t < 8 ? (mine ? 0 : 14) + t : (mine ? 8 : 22) + (t - 8);
+          const int f = plane * 81 + (side == 0 ? sq : 80 - sq);
+          atomicOr(&ws.oimg[f >> 5], 1u << (f & 31));
+        }
+      }
+      __syncwarp();
+    };
     auto write_obs = [&]() {
       if (!P.obs) return;
       // generate_neural_network_observation (shogi_game_io.py:434-539)
       float* orow = P.obs + (size_t)g * P.obs_stride;
+#if (KZ_ROWS_ONCE & 2)
+      {
+        // compose-once writer: every 32-byte piece of the row gets its final content in one store (no zero fill that is
+        // patched afterwards: profiles/row_store_probe.cu -- patching freshly zeroed sectors costs 7 % of the row
+        // bandwidth at 24 warps per SM).  Rows are 8-byte aligned: float2 head / tail around the 32-byte body.
+        build_obs_image();
+        float2* o2 = reinterpret_cast<float2*>(orow);
+        const int head = (int)(((32u - (unsigned)((uintptr_t)orow & 31)) & 31u) >> 3);
+        const int nb = (KZ_OBS_FLOATS * 4 - head * 8) >> 5;
+        char* body = reinterpret_cast<char*>(orow) + head * 8;
+        if (lane < head) {  // floats 0..5: plane 0
+          const uint32_t b2 = ws.oimg[0] >> (2 * lane);
+          o2[lane] = make_float2((b2 & 1) ? 1.0f : 0.f, (b2 & 2) ? 1.0f : 0.f);
+        }
+#pragma unroll 1
+        for (int q = lane; q < nb; q += 32) {
+          const int r0 = 2 * head + 8 * q;
+          char* dst = body + 32 * q;
+          if (r0 + 8 <= 28 * 81) {  // inside the piece planes: 8 bits of the image
+            const uint32_t bits = __funnelshift_r(ws.oimg[r0 >> 5], ws.oimg[(r0 >> 5) + 1], r0 & 31) & 0xFFu;
+            if (bits == 0) st_zero256(dst);
+            else {
+              uint32_t v[8];
+#pragma unroll
+              for (int k = 0; k < 8; k++) v[k] = ((bits >> k) & 1) ? 0x3F800000u : 0u;
+              st256(dst, v);
+            }
+          } else {
+            // constant planes: the piece lies in plane 28 + pl0, its floats from index nb0 on in the next plane
+            // (pl0 = -1: the seam piece, whose first nb0 floats are still piece-plane bits)
+            const int x = r0 - 28 * 81;
+            const int pl0 = x >= 0 ? (x * 1619) >> 17 : -1;  // floor(x / 81), x < 1700
+            const int nb0 = (pl0 + 1) * 81 - x;
+            const uint32_t a = pl0 >= 0 ? __float_as_uint(ws.opv[pl0]) : 0u, b = __float_as_uint(ws.opv[pl0 + 1]);
+            uint32_t bits = 0;
+            if (pl0 < 0) bits = __funnelshift_r(ws.oimg[r0 >> 5], ws.oimg[(r0 >> 5) + 1], r0 & 31) & ((1u << nb0) - 1u);
+            if (a == 0 && bits == 0 && (nb0 >= 8 || b == 0)) st_zero256(dst);
+            else {
+              uint32_t v[8];
+#pragma unroll
+              for (int k = 0; k < 8; k++) v[k] = k < nb0 ? (pl0 >= 0 ? a : (((bits >> k) & 1) ? 0x3F800000u : 0u)) : b;
+              st256(dst, v);
+            }
+          }
+        }
+        // the last floats of the row lie in plane 45, which is always zero (reserved; shogi_game_io.py:434-539)
+        const int tail0 = head + 4 * nb;
+        if (lane < KZ_OBS_FLOATS / 2 - tail0) o2[tail0 + lane] = make_float2(0.f, 0.f);
+        return;
+      }
+#endif
       // constant planes 28..45: value of plane 28+i lives in lane i
       float pv = 0.f;
       if (lane < 14) {
@@ -975,6 +1071,25 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
         // 16-byte chunk q of the row = bits [16q, 16q+16) of the bitmap; a from-square owns chunks 10f..10f+9.
         // Pass 1 zero-fills the 810 board-move chunks (256-bit stores on 32-byte aligned rows); pass 2 expands only the chunks
         // of from-squares that have a legal move (3 squares x 10 chunks per warp round) and the 36 drop chunks.
+#if (KZ_ROWS_ONCE & 1)
+        if ((((uintptr_t)mrow) & 31) == 0 && P.mask_stride >= 13536) {
+          // compose-once writer: 32-byte piece q of the row = the 32 actions of bitmap word q (pad bytes 13527..13535
+          // are written as zeros: the bitmap is zero-padded)
+          __syncwarp();
+#pragma unroll 1
+          for (int q = lane; q < 423; q += 32) {
+            const uint32_t w = ws.bitmap[q];
+            if (w == 0) st_zero256(mrow + 32 * q);
+            else {
+              uint32_t v[8];
+#pragma unroll
+              for (int k = 0; k < 8; k++) v[k] = (((w >> (4 * k)) & 0xF) * 0x00204081u) & 0x01010101u;
+              st256(mrow + 32 * q, v);
+            }
+          }
+          return;
+        }
+#endif
         uint4* m4 = reinterpret_cast<uint4*>(mrow);
         if (!KZ_FILL_AFTER_COMPACT && !(KZ_BULK_ZERO & 1)) fill_mask_zero();
         uint32_t act[3];
@@ -1102,16 +1217,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
     };
     // (Measured and not faster: choosing the next action before the mask row's store burst; writing the observation row
     // ahead of the move generation, +8 %.)
-    if constexpr (MODE == 2) {
+    if (MODE == 2 || P.bitmap_out) {  // rollout form: the legal set leaves as its 1,792-byte bitmap
       __syncwarp();
-      uint4* dst = reinterpret_cast<uint4*>(P.bitmap_out + (size_t)g * BITMAP_WORDS);
+      uint4* dst = reinterpret_cast<uint4*>(P.bitmap_out + (size_t)g * P.bitmap_stride);
       for (int i = lane; i < BITMAP_WORDS / 4; i += 32) dst[i] = reinterpret_cast<const uint4*>(ws.bitmap)[i];
-      pick_next();
-    } else {
-      write_mask();
-      pick_next();
-      write_obs();
     }
+    if constexpr (MODE != 2) write_mask();
+    pick_next();
+    write_obs();
 
     // ---- store state
     __syncwarp();
@@ -1276,6 +1389,26 @@ __global__ void __launch_bounds__(256) kz_expand_kernel(const uint8_t* __restric
   }
 }
 
+// Legal bitmap rows -> byte-mask rows (PolicyOutputMapper.get_legal_mask's layout, utils.py:310-336) for callers of the
+// reference API; any row stride / alignment (4 mask bytes per store when the row is 4-byte aligned).
+__global__ void __launch_bounds__(256) kz_bitmap_expand_kernel(const uint32_t* __restrict__ bitmap, long long ldb,
+                                                               const long long* __restrict__ rows, int n,
+                                                               uint8_t* __restrict__ mask, long long ldm) {
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (g >= n) return;
+  const uint32_t* bm = bitmap + (size_t)(rows ? rows[g] : g) * ldb;
+  uint8_t* mrow = mask + (size_t)g * ldm;
+  if ((((uintptr_t)mrow) & 3) == 0) {
+    uint32_t* m32 = reinterpret_cast<uint32_t*>(mrow);
+    for (int q = lane; q < KZ_NUM_ACTIONS / 4; q += 32)  // 4 actions per store
+      m32[q] = (((__ldg(bm + (q >> 3)) >> ((q & 7) * 4)) & 0xF) * 0x00204081u) & 0x01010101u;
+    for (int i = (KZ_NUM_ACTIONS / 4) * 4 + lane; i < KZ_NUM_ACTIONS; i += 32) mrow[i] = (uint8_t)((__ldg(bm + (i >> 5)) >> (i & 31)) & 1);
+  } else {
+    for (int i = lane; i < KZ_NUM_ACTIONS; i += 32) mrow[i] = (uint8_t)((__ldg(bm + (i >> 5)) >> (i & 31)) & 1);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 __global__ void kz_reset_kernel(uint8_t* boards, uint8_t* meta, uint4* rep, int rep_slots, int n,
                                 const uint8_t* env_mask, int max_moves) {
@@ -1413,8 +1546,10 @@ Layout layout(int n, int hist_cap) {
   return L;
 }
 
-int launch_step(void* state, int n, int hist_cap, StepParams P, cudaStream_t st) {
+int launch_step(void* state, int n, int hist_cap, StepParams P, cudaStream_t st, int first = 0, int count = -1, int slot = 0) {
   if (!state || n <= 0 || hist_cap < 0 || hist_cap > 65535) return KZ_E_ARG;
+  if (count < 0) count = n - first;
+  if (first < 0 || count <= 0 || first + count > n || slot < 0 || slot >= 64) return KZ_E_ARG;
   if (!g_host_ready) return KZ_E_NOT_INIT;
   if (((uintptr_t)state & 255) != 0) return KZ_E_ARG;
   const Layout L = layout(n, hist_cap);
@@ -1424,25 +1559,31 @@ int launch_step(void* state, int n, int hist_cap, StepParams P, cudaStream_t st)
   P.hist = reinterpret_cast<uint4*>(base + L.off_hist);
   P.rep_slots = L.rep_slots;
   P.hist_cap = hist_cap;
-  P.n = n;
+  P.n = count;
+  P.g_first = first;
   if (P.obs) {
     if (((uintptr_t)P.obs & 15) || (P.obs_stride & 1) || P.obs_stride < KZ_OBS_FLOATS) return KZ_E_ARG;
   }
+  if (P.bitmap_out) {
+    if (((uintptr_t)P.bitmap_out & 15) || P.bitmap_stride < BITMAP_WORDS || (P.bitmap_stride & 3)) return KZ_E_ARG;
+  } else if (P.mode == 2) return KZ_E_ARG;
   P.mask_vec = 0;
   if (P.mask) {
     if (P.mask_stride < KZ_NUM_ACTIONS) return KZ_E_ARG;
     P.mask_vec = (((uintptr_t)P.mask & 15) == 0 && (P.mask_stride & 15) == 0) ? 1 : 0;
-    if (n == 1 && ((uintptr_t)P.mask & 15) == 0) P.mask_vec = 1;
+    if (count == 1 && ((uintptr_t)P.mask & 15) == 0) P.mask_vec = 1;
   }
-  const int ctas_needed = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-  int grid = g_sm_count * (P.mode == 2 ? KZ_COMPACT_CTAS_PER_SM : CTAS_PER_SM);
+  const int ctas_needed = (count + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  // mode 2 without observation rows is the split pipeline's generator (leaves room for kz_expand_kernel beside it)
+  int grid = g_sm_count * ((P.mode == 2 && !P.obs) ? KZ_COMPACT_CTAS_PER_SM : CTAS_PER_SM);
   if (grid > ctas_needed) grid = ctas_needed;
   const size_t dyn = sizeof(WarpScratch) * WARPS_PER_CTA;
   P.tile_counter = nullptr;
 #ifndef KZ_STATIC_TILES
-  if (grid < ctas_needed && n % WARPS_PER_CTA == 0) {
-    // launches on one state buffer are ordered by their data dependence, so the counter can live in it
-    P.tile_counter = reinterpret_cast<int*>(base + L.off_sched);
+  if (grid < ctas_needed && count % WARPS_PER_CTA == 0) {
+    // launches on one state buffer are ordered by their data dependence, so the counter can live in it (launches over
+    // disjoint game ranges that run concurrently, kz_step_range, name different counter slots)
+    P.tile_counter = reinterpret_cast<int*>(base + L.off_sched) + slot;
     CK(cudaMemsetAsync(P.tile_counter, 0, sizeof(int), st));
   }
 #endif
@@ -1651,6 +1792,23 @@ int kz_step(void* state, int n, int hist_cap, const void* actions, int actions_i
   return launch_step(state, n, hist_cap, P, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int kz_step_range(void* state, int n, int hist_cap, int first, int count, int counter_slot, const void* actions,
+                  int actions_i64, float* obs, int64_t obs_stride, uint8_t* mask, int64_t mask_stride, uint32_t* bitmap,
+                  int64_t bitmap_stride_words, float* reward, uint8_t* done, uint8_t* reason, int8_t* winner, int32_t* ep_len,
+                  int32_t* legal_count, void* next_actions, uint64_t seed, uint32_t rng_step, uint32_t env_offset,
+                  int auto_reset, void* stream) {
+  if (!actions || (mask && bitmap)) return KZ_E_ARG;
+  StepParams P{};
+  P.actions = actions; P.actions_i64 = actions_i64;
+  P.obs = obs; P.obs_stride = obs_stride; P.mask = mask; P.mask_stride = mask_stride;
+  P.bitmap_out = bitmap; P.bitmap_stride = bitmap_stride_words;
+  P.reward = reward; P.done = done; P.reason = reason; P.winner = winner; P.ep_len = ep_len;
+  P.legal_count = legal_count; P.next_actions = next_actions;
+  P.seed = seed; P.rng_step = rng_step; P.env_offset = env_offset;
+  P.auto_reset = auto_reset; P.mode = bitmap ? 2 : 1;
+  return launch_step(state, n, hist_cap, P, reinterpret_cast<cudaStream_t>(stream), first, count, counter_slot);
+}
+
 int kz_step_compact(void* state, int n, int hist_cap, const void* actions, int actions_i64, uint32_t* bitmap,
                     float* reward, uint8_t* done, uint8_t* reason, int8_t* winner, int32_t* ep_len, int32_t* legal_count,
                     void* next_actions, uint64_t seed, uint32_t rng_step, uint32_t env_offset, int auto_reset,
@@ -1658,7 +1816,7 @@ int kz_step_compact(void* state, int n, int hist_cap, const void* actions, int a
   if (!actions || !bitmap || ((uintptr_t)bitmap & 15)) return KZ_E_ARG;
   StepParams P{};
   P.actions = actions; P.actions_i64 = actions_i64;
-  P.bitmap_out = bitmap;
+  P.bitmap_out = bitmap; P.bitmap_stride = BITMAP_WORDS;
   P.reward = reward; P.done = done; P.reason = reason; P.winner = winner; P.ep_len = ep_len;
   P.legal_count = legal_count; P.next_actions = next_actions;
   P.seed = seed; P.rng_step = rng_step; P.env_offset = env_offset;
@@ -1683,6 +1841,43 @@ int kz_expand(const void* state, int n, int hist_cap, const uint32_t* bitmap, fl
   if (grid > (n + 7) / 8) grid = (n + 7) / 8;
   kz_expand_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(base + L.off_boards, base + L.off_meta, bitmap, n,
                                                                             obs, obs_stride, mask, mask_stride, mask_vec);
+  CK(cudaGetLastError());
+  return KZ_OK;
+}
+
+int kz_step_rollout(void* state, int n, int hist_cap, const void* actions, int actions_i64, float* obs, int64_t obs_stride,
+                    uint32_t* bitmap, int64_t bitmap_stride_words, float* reward, uint8_t* done, uint8_t* reason,
+                    int8_t* winner, int32_t* ep_len, int32_t* legal_count, void* next_actions, uint64_t seed,
+                    uint32_t rng_step, uint32_t env_offset, int auto_reset, void* stream) {
+  if (!actions || !bitmap) return KZ_E_ARG;
+  StepParams P{};
+  P.actions = actions; P.actions_i64 = actions_i64;
+  P.obs = obs; P.obs_stride = obs_stride;
+  P.bitmap_out = bitmap; P.bitmap_stride = bitmap_stride_words;
+  P.reward = reward; P.done = done; P.reason = reason; P.winner = winner; P.ep_len = ep_len;
+  P.legal_count = legal_count; P.next_actions = next_actions;
+  P.seed = seed; P.rng_step = rng_step; P.env_offset = env_offset;
+  P.auto_reset = auto_reset; P.mode = 2;
+  return launch_step(state, n, hist_cap, P, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int kz_legal_bitmap(void* state, int n, int hist_cap, float* obs, int64_t obs_stride, uint32_t* bitmap,
+                    int64_t bitmap_stride_words, int32_t* legal_count, void* stream) {
+  if (!bitmap) return KZ_E_ARG;
+  StepParams P{};
+  P.obs = obs; P.obs_stride = obs_stride;
+  P.bitmap_out = bitmap; P.bitmap_stride = bitmap_stride_words;
+  P.legal_count = legal_count;
+  P.mode = 0;
+  return launch_step(state, n, hist_cap, P, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int kz_bitmap_expand(const uint32_t* bitmap, int64_t bitmap_stride_words, const int64_t* bitmap_rows, int n, uint8_t* mask,
+                     int64_t mask_stride, void* stream) {
+  if (!bitmap || !mask || n <= 0 || bitmap_stride_words < 423 || mask_stride < KZ_NUM_ACTIONS || ((uintptr_t)bitmap & 3))
+    return KZ_E_ARG;
+  kz_bitmap_expand_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      bitmap, bitmap_stride_words, reinterpret_cast<const long long*>(bitmap_rows), n, mask, mask_stride);
   CK(cudaGetLastError());
   return KZ_OK;
 }

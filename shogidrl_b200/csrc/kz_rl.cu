@@ -33,10 +33,11 @@ __device__ __forceinline__ uint32_t hash_u32(unsigned long long seed, unsigned l
 // logits only at legal entries.  A row is cut into 16-byte windows aligned in memory (whatever the row's own
 // alignment); the partial windows at both ends are assembled from byte loads, so no access leaves the row.
 struct MaskWindows {
+  typedef uint4 Raw;
   const uint8_t* row;
   int shift;  // row address minus the aligned address of window 0
   int nw;
-  __device__ __forceinline__ explicit MaskWindows(const uint8_t* r) : row(r) {
+  __device__ __forceinline__ explicit MaskWindows(const void* r) : row(reinterpret_cast<const uint8_t*>(r)) {
     shift = (int)(reinterpret_cast<uintptr_t>(r) & 15);
     nw = (KZ_NUM_ACTIONS + shift + 15) >> 4;
   }
@@ -59,6 +60,35 @@ struct MaskWindows {
     }
     return v;
   }
+  // bit b of the result = byte b of the window is non-zero
+  static __device__ __forceinline__ uint32_t bits16(const uint4& v) {
+    if (!(v.x | v.y | v.z | v.w)) return 0u;
+    // one bit per byte (bit 0 of each byte of the compare result), gathered into a nibble by a carry-free multiply
+    auto nib = [](uint32_t x) { return ((__vcmpne4(x, 0) & 0x01010101u) * 0x01020408u) >> 24; };
+    return nib(v.x) | (nib(v.y) << 4) | (nib(v.z) << 8) | (nib(v.w) << 12);
+  }
+  __device__ __forceinline__ bool legal(long long a) const { return row[a] != 0; }
+};
+
+// The same windows over a row of the engine's legal BITMAP (kz_step_rollout / kz_legal_bitmap: bit i of the 448-word
+// row = action i is legal; 1,792 bytes instead of 13,527).  Window w = bits [16w, 16w + 16) = one half of word w >> 1,
+// so the compacted list -- and with it every sum, the sampled action and every gradient -- is the one the byte-mask
+// scan of a 16-byte aligned row produces, bit for bit.
+struct BitmapWindows {
+  typedef uint32_t Raw;
+  const uint32_t* row;
+  int nw;
+  __device__ __forceinline__ explicit BitmapWindows(const void* r) : row(reinterpret_cast<const uint32_t*>(r)) {
+    nw = (KZ_NUM_ACTIONS + 15) >> 4;
+  }
+  __device__ __forceinline__ int first(int w) const { return w << 4; }
+  __device__ __forceinline__ uint32_t load(int w) const {
+    if (w >= nw) return 0u;
+    const uint32_t x = __ldg(row + (w >> 1));
+    return (w & 1) ? (x >> 16) : (x & 0xFFFFu);
+  }
+  static __device__ __forceinline__ uint32_t bits16(uint32_t v) { return v; }
+  __device__ __forceinline__ bool legal(long long a) const { return (row[a >> 5] >> (a & 31)) & 1u; }
 };
 
 // Compacted list of a row's legal actions in the warp's shared-memory slice.  Scanning the mask lane by lane and
@@ -75,29 +105,24 @@ struct LegalList {
 
 // f(action index) for every legal action of the row, a fixed order, all lanes taking list entries round-robin
 // (entry j of a piece goes to lane j % 32)
-template <class F>
-__device__ __forceinline__ void each_legal_of_row(const MaskWindows& W, int lane, LegalList& ll, F&& f) {
+template <class WIN, class F>
+__device__ __forceinline__ void each_legal_of_row(const WIN& W, int lane, LegalList& ll, F&& f) {
   if (!ll.whole) {
     ll.cnt = 0;
     bool flushed = false;
-    uint4 nx[MASK_MLP];  // next group's windows, loaded one group ahead of their compaction
+    typename WIN::Raw nx[MASK_MLP];  // next group's windows, loaded one group ahead of their compaction
 #pragma unroll
     for (int k = 0; k < MASK_MLP; k++) nx[k] = W.load(lane + 32 * k);
     for (int w0 = lane; w0 - lane < W.nw; w0 += 32 * MASK_MLP) {
-      uint4 v[MASK_MLP];
+      uint32_t v[MASK_MLP];  // 16 legality bits per window
 #pragma unroll
       for (int k = 0; k < MASK_MLP; k++) {
-        v[k] = nx[k];
+        v[k] = WIN::bits16(nx[k]);
         nx[k] = W.load(w0 + 32 * (MASK_MLP + k));
       }
       int c = 0;
 #pragma unroll
-      for (int k = 0; k < MASK_MLP; k++) {
-        if (!(v[k].x | v[k].y | v[k].z | v[k].w)) continue;
-        v[k].x = __vcmpne4(v[k].x, 0); v[k].y = __vcmpne4(v[k].y, 0);
-        v[k].z = __vcmpne4(v[k].z, 0); v[k].w = __vcmpne4(v[k].w, 0);
-        c += (__popc(v[k].x) + __popc(v[k].y) + __popc(v[k].z) + __popc(v[k].w)) >> 3;
-      }
+      for (int k = 0; k < MASK_MLP; k++) c += __popc(v[k]);
       int incl = c;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
@@ -112,17 +137,12 @@ __device__ __forceinline__ void each_legal_of_row(const MaskWindows& W, int lane
       int at = ll.cnt + incl - c;
 #pragma unroll
       for (int k = 0; k < MASK_MLP; k++) {
-        if (!(v[k].x | v[k].y | v[k].z | v[k].w)) continue;
-        const uint32_t q[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+        uint32_t z = v[k];
         const int lo = W.first(w0 + 32 * k);
-#pragma unroll
-        for (int h = 0; h < 4; h++) {
-          uint32_t z = q[h];
-          while (z) {
-            const int b = (__ffs(z) - 1) >> 3;
-            z &= ~(0xFFu << (b * 8));
-            ll.buf[at++] = (uint16_t)(lo + h * 4 + b);
-          }
+        while (z) {
+          const int b = __ffs(z) - 1;
+          z &= z - 1;
+          ll.buf[at++] = (uint16_t)(lo + b);
         }
       }
       ll.cnt += total;
@@ -137,7 +157,8 @@ __device__ __forceinline__ void each_legal_of_row(const MaskWindows& W, int lane
 // One warp per row.  Element order for the inverse CDF: lane-major over the mask windows (lane 0's windows
 // 0, 32, 64, ... in ascending action order, then lane 1's, ...), a fixed permutation of the action axis, so the
 // sampled law is the masked softmax.
-__global__ void __launch_bounds__(256, 4) kz_sample_kernel(const void* logits, int bf16, long long ld, const uint8_t* mask,
+template <class WIN>  // MaskWindows: byte mask rows; BitmapWindows: 448-word legal bitmap rows.  ldm in bytes.
+__global__ void __launch_bounds__(256, 4) kz_sample_kernel(const void* logits, int bf16, long long ld, const void* mask,
                                                         long long ldm, int n, unsigned long long seed,
                                                         unsigned long long offset, void* actions, int actions_i64,
                                                         float* logp, float* entropy, int deterministic) {
@@ -145,7 +166,7 @@ __global__ void __launch_bounds__(256, 4) kz_sample_kernel(const void* logits, i
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
   const char* lrow = reinterpret_cast<const char*>(logits) + (size_t)row * ld * (bf16 ? 2 : 4);
-  const MaskWindows W(mask + (size_t)row * ldm);
+  const WIN W(reinterpret_cast<const char*>(mask) + (size_t)row * ldm);
   __shared__ uint16_t s_list[8][LIST_CAP];
   LegalList ll{s_list[threadIdx.x >> 5], 0, false};
   const int A = KZ_NUM_ACTIONS;
@@ -312,15 +333,15 @@ __device__ __forceinline__ float ent_g(float p, float eps) {  // dH/dp for H = -
   return -(logf(p) + 1.0f);
 }
 
-__global__ void __launch_bounds__(256, 4) kz_eval_fwd_kernel(const void* logits, int bf16, long long ld, const uint8_t* mask,
+template <class WIN>
+__global__ void __launch_bounds__(256, 4) kz_eval_fwd_kernel(const void* logits, int bf16, long long ld, const void* mask,
                                                           long long ldm, const long long* mask_rows, const long long* actions,
                                                           int n, float* logp, float* entropy, float* saved /*[n][4]*/) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
   const char* lrow = reinterpret_cast<const char*>(logits) + (size_t)row * ld * (bf16 ? 2 : 4);
-  const uint8_t* mrow = mask + (size_t)(mask_rows ? mask_rows[row] : row) * ldm;
-  const MaskWindows W(mrow);
+  const WIN W(reinterpret_cast<const char*>(mask) + (size_t)(mask_rows ? mask_rows[row] : row) * ldm);
   __shared__ uint16_t s_list[8][LIST_CAP];
   LegalList ll{s_list[threadIdx.x >> 5], 0, false};
   const int A = KZ_NUM_ACTIONS;
@@ -356,7 +377,7 @@ __global__ void __launch_bounds__(256, 4) kz_eval_fwd_kernel(const void* logits,
     ent = h; S = sg;
     const long long a = actions[row];
     float pa = 0.f;
-    if (a >= 0 && a < A && mrow[a]) pa = expf(ld_logit(lrow, (int)a, bf16) - M) * inv;
+    if (a >= 0 && a < A && W.legal(a)) pa = expf(ld_logit(lrow, (int)a, bf16) - M) * inv;
     lp = logf(fminf(fmaxf(pa, eps), 1.0f - eps));
   }
   if (lane == 0) {
@@ -376,15 +397,16 @@ __device__ __forceinline__ void zero_row(char* p, size_t bytes, int lane) {
   if ((size_t)lane * 2 < tail) *reinterpret_cast<uint16_t*>(p + head + body + lane * 2) = 0;
 }
 
-__global__ void __launch_bounds__(256, 4) kz_eval_bwd_kernel(const void* logits, int bf16, long long ld, const uint8_t* mask,
+template <class WIN>
+__global__ void __launch_bounds__(256, 4) kz_eval_bwd_kernel(const void* logits, int bf16, long long ld, const void* mask,
                                                           long long ldm, const long long* mask_rows, const long long* actions,
                                                           int n, const float* dlogp, const float* dent, const float* saved,
-                                                          void* dlogits, long long ldg, float* dbias) {
+                                                          void* dlogits, long long ldg, long long* dbias_q44) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
   const char* lrow = reinterpret_cast<const char*>(logits) + (size_t)row * ld * (bf16 ? 2 : 4);
-  const uint8_t* mrow = mask + (size_t)(mask_rows ? mask_rows[row] : row) * ldm;
+  const WIN W(reinterpret_cast<const char*>(mask) + (size_t)(mask_rows ? mask_rows[row] : row) * ldm);
   char* grow = reinterpret_cast<char*>(dlogits) + (size_t)row * ldg * (bf16 ? 2 : 4);
   const int A = KZ_NUM_ACTIONS;
   const float eps = FLT_EPSILON;
@@ -394,14 +416,13 @@ __global__ void __launch_bounds__(256, 4) kz_eval_bwd_kernel(const void* logits,
   const float inv = dead ? 0.f : 1.0f / Z;
   const long long a = actions[row];
   float pa = 0.f;
-  if (!dead && a >= 0 && a < A && mrow[a]) pa = expf(ld_logit(lrow, (int)a, bf16) - M) * inv;
+  if (!dead && a >= 0 && a < A && W.legal(a)) pa = expf(ld_logit(lrow, (int)a, bf16) - M) * inv;
   const float wl = (pa > eps && pa < 1.0f - eps) ? gl : 0.f;  // clamp passes gradient only inside (eps, 1 - eps)
   // dlogits is zero except at legal actions: clear the row with 16-byte stores, then scatter the legal entries
   const int esz = bf16 ? 2 : 4;
   zero_row(grow, (size_t)A * esz, lane);
   if (dead) return;
   __syncwarp();  // orders the clearing stores before the scattered ones (different lanes, same addresses)
-  const MaskWindows W(mrow);
   __shared__ uint16_t s_list[8][LIST_CAP];
   LegalList ll{s_list[threadIdx.x >> 5], 0, false};
   each_legal_of_row(W, lane, ll, [&](int i) {
@@ -409,7 +430,11 @@ __global__ void __launch_bounds__(256, 4) kz_eval_bwd_kernel(const void* logits,
     const float g = ge * p * (ent_g(p, eps) - S) + wl * ((i == a ? 1.f : 0.f) - p);
     if (bf16) reinterpret_cast<__nv_bfloat16*>(grow)[i] = __float2bfloat16(g);
     else reinterpret_cast<float*>(grow)[i] = g;
-    if (dbias) atomicAdd(dbias + i, g);  // column sum = bias gradient of the policy head (result unused: RED in L2)
+    // column sum = bias gradient of the policy head, accumulated in Q20.44 fixed point: integer addition is
+    // associative, so the result does not depend on the order the rows arrive in (an fp32 atomicAdd does); scaling by
+    // 2^44 is exact in fp32 and |g| <= ~2 keeps 2^20 rows away from overflow (result unused: RED in L2)
+    if (dbias_q44) atomicAdd(reinterpret_cast<unsigned long long*>(dbias_q44) + i,
+                             (unsigned long long)__float2ll_rn(ldexpf(g, 44)));
   });
 }
 
@@ -481,14 +506,36 @@ __global__ void __launch_bounds__(1024) kz_ppo_loss_kernel(const float* __restri
 
 extern "C" {
 
+static int sample_impl(const void* logits, int logits_bf16, int64_t ld, const void* mask, int64_t ldm_bytes, int bitmap, int n,
+                       uint64_t seed, uint64_t offset, void* actions, int actions_i64, float* logp, float* entropy,
+                       int deterministic, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (bitmap)
+    kz_sample_kernel<BitmapWindows><<<(n + 7) / 8, 256, 0, st>>>(logits, logits_bf16, ld, mask, ldm_bytes, n, seed, offset,
+                                                                  actions, actions_i64, logp, entropy, deterministic);
+  else
+    kz_sample_kernel<MaskWindows><<<(n + 7) / 8, 256, 0, st>>>(logits, logits_bf16, ld, mask, ldm_bytes, n, seed, offset,
+                                                                actions, actions_i64, logp, entropy, deterministic);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? KZ_OK : fail(e);
+}
+
 int kz_sample_masked(const void* logits, int logits_bf16, int64_t ld, const uint8_t* mask, int64_t ldm, int n,
                      uint64_t seed, uint64_t offset, void* actions, int actions_i64, float* logp, float* entropy,
                      int deterministic, void* stream) {
   if (!logits || !mask || !actions || n <= 0 || ld < KZ_NUM_ACTIONS || ldm < KZ_NUM_ACTIONS) return KZ_E_ARG;
-  kz_sample_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      logits, logits_bf16, ld, mask, ldm, n, seed, offset, actions, actions_i64, logp, entropy, deterministic);
-  cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? KZ_OK : fail(e);
+  return sample_impl(logits, logits_bf16, ld, mask, ldm, 0, n, seed, offset, actions, actions_i64, logp, entropy,
+                     deterministic, stream);
+}
+
+int kz_sample_bitmap(const void* logits, int logits_bf16, int64_t ld, const uint32_t* bitmap, int64_t ldb_words, int n,
+                     uint64_t seed, uint64_t offset, void* actions, int actions_i64, float* logp, float* entropy,
+                     int deterministic, void* stream) {
+  if (!logits || !bitmap || !actions || n <= 0 || ld < KZ_NUM_ACTIONS || ldb_words < KZ_BITMAP_WORDS_MIN ||
+      ((uintptr_t)bitmap & 3))
+    return KZ_E_ARG;
+  return sample_impl(logits, logits_bf16, ld, bitmap, ldb_words * 4, 1, n, seed, offset, actions, actions_i64, logp, entropy,
+                     deterministic, stream);
 }
 
 int kz_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_value, int T, int N,
@@ -506,16 +553,55 @@ int kz_gae(const float* rewards, const float* values, const uint8_t* dones, cons
   return e == cudaSuccess ? KZ_OK : fail(e);
 }
 
+static int eval_fwd_impl(const void* logits, int logits_bf16, int64_t ld, const void* mask, int64_t ldm_bytes, int bitmap,
+                         const int64_t* mask_rows, const int64_t* actions, int n, float* logp, float* entropy,
+                         float* saved4, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long* mr = reinterpret_cast<const long long*>(mask_rows);
+  const long long* ac = reinterpret_cast<const long long*>(actions);
+  if (bitmap)
+    kz_eval_fwd_kernel<BitmapWindows><<<(n + 7) / 8, 256, 0, st>>>(logits, logits_bf16, ld, mask, ldm_bytes, mr, ac, n, logp,
+                                                                    entropy, saved4);
+  else
+    kz_eval_fwd_kernel<MaskWindows><<<(n + 7) / 8, 256, 0, st>>>(logits, logits_bf16, ld, mask, ldm_bytes, mr, ac, n, logp,
+                                                                  entropy, saved4);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? KZ_OK : fail(e);
+}
+
+static int eval_bwd_impl(const void* logits, int logits_bf16, int64_t ld, const void* mask, int64_t ldm_bytes, int bitmap,
+                         const int64_t* mask_rows, const int64_t* actions, int n, const float* dlogp, const float* dentropy,
+                         const float* saved4, void* dlogits, int64_t ldg, int64_t* dbias_q44, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long* mr = reinterpret_cast<const long long*>(mask_rows);
+  const long long* ac = reinterpret_cast<const long long*>(actions);
+  long long* db = reinterpret_cast<long long*>(dbias_q44);
+  if (bitmap)
+    kz_eval_bwd_kernel<BitmapWindows><<<(n + 7) / 8, 256, 0, st>>>(logits, logits_bf16, ld, mask, ldm_bytes, mr, ac, n, dlogp,
+                                                                    dentropy, saved4, dlogits, ldg, db);
+  else
+    kz_eval_bwd_kernel<MaskWindows><<<(n + 7) / 8, 256, 0, st>>>(logits, logits_bf16, ld, mask, ldm_bytes, mr, ac, n, dlogp,
+                                                                  dentropy, saved4, dlogits, ldg, db);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? KZ_OK : fail(e);
+}
+
 int kz_eval_masked_fwd(const void* logits, int logits_bf16, int64_t ld, const uint8_t* mask, int64_t ldm,
                        const int64_t* mask_rows, const int64_t* actions, int n, float* logp, float* entropy, float* saved4,
                        void* stream) {
   if (!logits || !mask || !actions || !logp || !entropy || !saved4 || n <= 0 || ld < KZ_NUM_ACTIONS || ldm < KZ_NUM_ACTIONS)
     return KZ_E_ARG;
-  kz_eval_fwd_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      logits, logits_bf16, ld, mask, ldm, reinterpret_cast<const long long*>(mask_rows),
-      reinterpret_cast<const long long*>(actions), n, logp, entropy, saved4);
-  cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? KZ_OK : fail(e);
+  return eval_fwd_impl(logits, logits_bf16, ld, mask, ldm, 0, mask_rows, actions, n, logp, entropy, saved4, stream);
+}
+
+int kz_eval_bitmap_fwd(const void* logits, int logits_bf16, int64_t ld, const uint32_t* bitmap, int64_t ldb_words,
+                       const int64_t* bitmap_rows, const int64_t* actions, int n, float* logp, float* entropy, float* saved4,
+                       void* stream) {
+  if (!logits || !bitmap || !actions || !logp || !entropy || !saved4 || n <= 0 || ld < KZ_NUM_ACTIONS ||
+      ldb_words < KZ_BITMAP_WORDS_MIN || ((uintptr_t)bitmap & 3))
+    return KZ_E_ARG;
+  return eval_fwd_impl(logits, logits_bf16, ld, bitmap, ldb_words * 4, 1, bitmap_rows, actions, n, logp, entropy, saved4,
+                       stream);
 }
 
 int kz_eval_masked_bwd(const void* logits, int logits_bf16, int64_t ld, const uint8_t* mask, int64_t ldm,
@@ -524,25 +610,29 @@ int kz_eval_masked_bwd(const void* logits, int logits_bf16, int64_t ld, const ui
   if (!logits || !mask || !actions || !dlogp || !dentropy || !saved4 || !dlogits || n <= 0 || ld < KZ_NUM_ACTIONS ||
       ldm < KZ_NUM_ACTIONS || ldg < KZ_NUM_ACTIONS)
     return KZ_E_ARG;
-  kz_eval_bwd_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      logits, logits_bf16, ld, mask, ldm, reinterpret_cast<const long long*>(mask_rows),
-      reinterpret_cast<const long long*>(actions), n, dlogp, dentropy, saved4, dlogits, ldg, nullptr);
-  cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? KZ_OK : fail(e);
+  return eval_bwd_impl(logits, logits_bf16, ld, mask, ldm, 0, mask_rows, actions, n, dlogp, dentropy, saved4, dlogits, ldg,
+                       nullptr, stream);
 }
 
 int kz_eval_masked_bwd_bias(const void* logits, int logits_bf16, int64_t ld, const uint8_t* mask, int64_t ldm,
                             const int64_t* mask_rows, const int64_t* actions, int n, const float* dlogp,
-                            const float* dentropy, const float* saved4, void* dlogits, int64_t ldg, float* dbias,
+                            const float* dentropy, const float* saved4, void* dlogits, int64_t ldg, int64_t* dbias_q44,
                             void* stream) {
-  if (!logits || !mask || !actions || !dlogp || !dentropy || !saved4 || !dlogits || !dbias || n <= 0 ||
-      ld < KZ_NUM_ACTIONS || ldm < KZ_NUM_ACTIONS || ldg < KZ_NUM_ACTIONS)
+  if (!logits || !mask || !actions || !dlogp || !dentropy || !saved4 || !dlogits || !dbias_q44 || n <= 0 ||
+      ld < KZ_NUM_ACTIONS || ldm < KZ_NUM_ACTIONS || ldg < KZ_NUM_ACTIONS || ((uintptr_t)dbias_q44 & 7))
     return KZ_E_ARG;
-  kz_eval_bwd_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      logits, logits_bf16, ld, mask, ldm, reinterpret_cast<const long long*>(mask_rows),
-      reinterpret_cast<const long long*>(actions), n, dlogp, dentropy, saved4, dlogits, ldg, dbias);
-  cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? KZ_OK : fail(e);
+  return eval_bwd_impl(logits, logits_bf16, ld, mask, ldm, 0, mask_rows, actions, n, dlogp, dentropy, saved4, dlogits, ldg,
+                       dbias_q44, stream);
+}
+
+int kz_eval_bitmap_bwd(const void* logits, int logits_bf16, int64_t ld, const uint32_t* bitmap, int64_t ldb_words,
+                       const int64_t* bitmap_rows, const int64_t* actions, int n, const float* dlogp, const float* dentropy,
+                       const float* saved4, void* dlogits, int64_t ldg, int64_t* dbias_q44, void* stream) {
+  if (!logits || !bitmap || !actions || !dlogp || !dentropy || !saved4 || !dlogits || n <= 0 || ld < KZ_NUM_ACTIONS ||
+      ldb_words < KZ_BITMAP_WORDS_MIN || ldg < KZ_NUM_ACTIONS || ((uintptr_t)bitmap & 3) || ((uintptr_t)dbias_q44 & 7))
+    return KZ_E_ARG;
+  return eval_bwd_impl(logits, logits_bf16, ld, bitmap, ldb_words * 4, 1, bitmap_rows, actions, n, dlogp, dentropy, saved4,
+                       dlogits, ldg, dbias_q44, stream);
 }
 
 /* exact column kernel regardless of N (tests / bit-exact comparisons) */

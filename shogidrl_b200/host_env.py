@@ -25,7 +25,7 @@ class HostPipelinedEnv:
         self.n, self.G, self.ng = int(num_envs), int(groups), int(num_envs) // int(groups)
         self.envs: List[VecShogiEnv] = [
             VecShogiEnv(self.ng, max_moves_per_game, self.device, seed=seed, env_offset=env_offset + g * self.ng,
-                        auto_reset=auto_reset) for g in range(self.G)]
+                        auto_reset=auto_reset, step_streams=1) for g in range(self.G)]  # the groups already overlap
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.G)]
         self.events = [torch.cuda.Event() for _ in range(self.G)]
         self.d_actions = [torch.zeros(self.ng, dtype=torch.int64, device=self.device) for _ in range(self.G)]

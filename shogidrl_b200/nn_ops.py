@@ -20,6 +20,10 @@ from . import _native as nv
 _LD = (nv.NUM_ACTIONS + 15) // 16 * 16
 
 
+def _is_bitmap(mask: torch.Tensor) -> bool:
+    return mask.dtype == torch.int32 and mask.shape[-1] == nv.BITMAP_WORDS
+
+
 class _ObsConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, obs, weight, bias, relu, rows):
@@ -93,9 +97,10 @@ class _PolicyHeadEval(torch.autograd.Function):
         actions = actions.contiguous().long()
         if mask_rows is not None:
             mask_rows = mask_rows.contiguous().long()
-        nv.check(nv.lib().kz_eval_masked_fwd(logits.data_ptr(), 1, _LD, mask.data_ptr(), mask.stride(0), nv.ptr(mask_rows),
-                                             actions.data_ptr(), n, logp.data_ptr(), ent.data_ptr(), saved.data_ptr(),
-                                             nv.stream_ptr(dev)), "kz_eval_masked_fwd")
+        fwd = nv.lib().kz_eval_bitmap_fwd if _is_bitmap(mask) else nv.lib().kz_eval_masked_fwd
+        nv.check(fwd(logits.data_ptr(), 1, _LD, mask.data_ptr(), mask.stride(0), nv.ptr(mask_rows),
+                     actions.data_ptr(), n, logp.data_ptr(), ent.data_ptr(), saved.data_ptr(),
+                     nv.stream_ptr(dev)), "kz_eval_masked_fwd")
         ctx.save_for_backward(hb, wp, logits, mask, mask_rows, actions, saved)
         ctx.has_bias, ctx.hdtype, ctx.wdtype = bias is not None, h.dtype, weight.dtype
         return logp, ent
@@ -108,23 +113,28 @@ class _PolicyHeadEval(torch.autograd.Function):
         dlogits = torch.empty((n, _LD), dtype=torch.bfloat16, device=dev)
         dlogits[:, nv.NUM_ACTIONS:].zero_()                             # the kernel clears and fills [0, 13527)
         want_db = ctx.has_bias and ctx.needs_input_grad[2]
-        # bias gradient = column sums of dlogits: scatter-added by the same kernel (only legal entries are non-zero)
-        db32 = torch.zeros(_LD, dtype=torch.float32, device=dev) if want_db else None
+        # bias gradient = column sums of dlogits: scatter-added by the same kernel (only legal entries are non-zero) as
+        # Q20.44 fixed-point integers -- associative, hence deterministic run to run
+        dbq = torch.zeros(_LD, dtype=torch.int64, device=dev) if want_db else None
         common = (logits.data_ptr(), 1, _LD, mask.data_ptr(), mask.stride(0), nv.ptr(mask_rows), actions.data_ptr(), n,
                   dlogp.contiguous().float().data_ptr(), dent.contiguous().float().data_ptr(), saved.data_ptr(),
                   dlogits.data_ptr(), _LD)
-        if want_db:
-            nv.check(nv.lib().kz_eval_masked_bwd_bias(*common, db32.data_ptr(), nv.stream_ptr(dev)), "kz_eval_masked_bwd_bias")
+        if _is_bitmap(mask):
+            nv.check(nv.lib().kz_eval_bitmap_bwd(*common, nv.ptr(dbq), nv.stream_ptr(dev)), "kz_eval_bitmap_bwd")
+        elif want_db:
+            nv.check(nv.lib().kz_eval_masked_bwd_bias(*common, dbq.data_ptr(), nv.stream_ptr(dev)), "kz_eval_masked_bwd_bias")
         else:
             nv.check(nv.lib().kz_eval_masked_bwd(*common, nv.stream_ptr(dev)), "kz_eval_masked_bwd")
         dh = torch.mm(dlogits, wp).to(ctx.hdtype) if ctx.needs_input_grad[0] else None
         dw = torch.mm(dlogits.t(), hb)[: nv.NUM_ACTIONS].to(ctx.wdtype) if ctx.needs_input_grad[1] else None
-        db = db32[: nv.NUM_ACTIONS].to(ctx.wdtype) if want_db else None
+        db = (dbq[: nv.NUM_ACTIONS].to(torch.float64) * 2.0 ** -44).to(ctx.wdtype) if want_db else None
         return dh, dw, db, None, None, None
 
 
 def policy_head_evaluate(h: torch.Tensor, linear: torch.nn.Linear, mask: torch.Tensor, actions: torch.Tensor,
                          mask_rows: Optional[torch.Tensor] = None):
     """(log-prob of ``actions``, entropy) of softmax(mask(linear(h))) for a [B, K] feature batch, bf16 GEMMs."""
-    nv.require(linear.out_features == nv.NUM_ACTIONS and mask.stride(-1) == 1 and mask.dtype in (torch.uint8, torch.bool), "linear.out_features == nv.NUM_ACTIONS and mask.stride(-1) == 1 and mask.dtype in (torch.uint8, torch.bool)")
+    nv.require(linear.out_features == nv.NUM_ACTIONS and mask.stride(-1) == 1
+               and (mask.dtype in (torch.uint8, torch.bool) or _is_bitmap(mask)),
+               "policy_head_evaluate: 13,527-wide head and bool/uint8 mask rows or int32 [B, 448] legal bitmap rows")
     return _PolicyHeadEval.apply(h, linear.weight, linear.bias, mask, mask_rows, actions)

@@ -10,26 +10,73 @@ import torch
 from . import _native as nv
 
 
+def is_bitmap(mask: torch.Tensor) -> bool:
+    """A legal set given as the engine's bitmap rows (int32 [..., 448], bit i of a row = action i legal; what
+    ``VecShogiEnv.step_rollout`` writes) rather than as PolicyOutputMapper.get_legal_mask's byte rows."""
+    return mask.dtype == torch.int32 and mask.shape[-1] == nv.BITMAP_WORDS
+
+
+def _check_legal_rows(mask: torch.Tensor, what: str) -> None:
+    if is_bitmap(mask):
+        nv.require(mask.dim() == 2 and mask.stride(1) == 1 and mask.stride(0) >= nv.BITMAP_WORDS and mask.data_ptr() % 4 == 0,
+                   f"{what}: bitmap rows must be contiguous int32 [B, {nv.BITMAP_WORDS}]")
+    else:
+        nv.require(mask.dim() == 2 and mask.shape[1] == nv.NUM_ACTIONS and mask.stride(1) == 1
+                   and mask.dtype in (torch.uint8, torch.bool),
+                   f"{what}: expected bool/uint8 [B, {nv.NUM_ACTIONS}] rows or an int32 [B, {nv.BITMAP_WORDS}] legal bitmap")
+
+
 def sample_masked(logits: torch.Tensor, mask: torch.Tensor, seed: int = 0, offset: int = 0,
-                  deterministic: bool = False, want_entropy: bool = False
+                  deterministic: bool = False, want_entropy: bool = False,
+                  out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
                   ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
     """Masked softmax -> Categorical sample (argmax if deterministic) -> log_prob, one warp per row.
 
     Mirrors BaseActorCriticModel.get_action_and_value after forward() (base_actor_critic.py:64-116):
-    illegal logits -> -inf, softmax, NaN rows -> uniform, Categorical(probs) with its eps clamp."""
+    illegal logits -> -inf, softmax, NaN rows -> uniform, Categorical(probs) with its eps clamp.  ``mask`` is the
+    byte mask [n, 13527] or the engine's legal bitmap [n, 448] int32 (kz_sample_bitmap: identical results, 7.5x fewer
+    mask bytes).  ``out`` = (actions int64 [n], log_probs fp32 [n]) writes straight into rollout storage."""
     dev = nv.require_cuda(logits.device)
     nv.require(logits.dim() == 2 and logits.shape[1] == nv.NUM_ACTIONS and logits.stride(1) == 1, "logits.dim() == 2 and logits.shape[1] == nv.NUM_ACTIONS and logits.stride(1) == 1")
     nv.require(logits.dtype in (torch.float32, torch.bfloat16), "logits.dtype in (torch.float32, torch.bfloat16)")
-    nv.require(mask.shape == logits.shape and mask.stride(1) == 1 and mask.dtype in (torch.uint8, torch.bool), "mask.shape == logits.shape and mask.stride(1) == 1 and mask.dtype in (torch.uint8, torch.bool)")
+    _check_legal_rows(mask, "mask")
     n = logits.shape[0]
-    actions = torch.empty(n, dtype=torch.int64, device=dev)
-    logp = torch.empty(n, dtype=torch.float32, device=dev)
+    nv.require(mask.shape[0] == n, "mask.shape[0] == logits.shape[0]")
+    if out is not None:
+        actions, logp = out
+        nv.require(actions.dtype == torch.int64 and logp.dtype == torch.float32 and actions.is_contiguous()
+                   and logp.is_contiguous() and actions.numel() >= n and logp.numel() >= n and actions.device == dev
+                   and logp.device == dev, "out: (int64 [n], float32 [n]) contiguous tensors on the logits' device")
+    else:
+        actions = torch.empty(n, dtype=torch.int64, device=dev)
+        logp = torch.empty(n, dtype=torch.float32, device=dev)
     ent = torch.empty(n, dtype=torch.float32, device=dev) if want_entropy else None
-    nv.check(nv.lib().kz_sample_masked(logits.data_ptr(), int(logits.dtype == torch.bfloat16), logits.stride(0),
-                                       mask.data_ptr(), mask.stride(0), n, int(seed), int(offset), actions.data_ptr(), 1,
-                                       logp.data_ptr(), nv.ptr(ent), int(deterministic), nv.stream_ptr(dev)),
+    fn = nv.lib().kz_sample_bitmap if is_bitmap(mask) else nv.lib().kz_sample_masked
+    nv.check(fn(logits.data_ptr(), int(logits.dtype == torch.bfloat16), logits.stride(0),
+                mask.data_ptr(), mask.stride(0), n, int(seed), int(offset), actions.data_ptr(), 1,
+                logp.data_ptr(), nv.ptr(ent), int(deterministic), nv.stream_ptr(dev)),
              "kz_sample_masked")
     return actions, logp, ent
+
+
+def bitmap_to_mask(bitmap: torch.Tensor, rows: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None
+                   ) -> torch.Tensor:
+    """bool [B, 13527] legal masks (PolicyOutputMapper.get_legal_mask's layout, utils.py:310-336) from legal bitmap
+    rows ``bitmap[rows]`` (or every row): the view API callers of ``ExperienceBuffer.legal_masks`` expect."""
+    dev = nv.require_cuda(bitmap.device)
+    _check_legal_rows(bitmap, "bitmap")
+    nv.require(is_bitmap(bitmap), "bitmap: int32 [B, 448]")
+    if rows is not None:
+        rows = rows.to(device=dev, dtype=torch.int64).contiguous()
+    n = bitmap.shape[0] if rows is None else rows.numel()
+    if out is None:
+        out = torch.empty((n, nv.NUM_ACTIONS), dtype=torch.bool, device=dev)
+    nv.require(out.dim() == 2 and out.shape[0] >= n and out.shape[1] == nv.NUM_ACTIONS and out.stride(1) == 1
+               and out.dtype in (torch.bool, torch.uint8) and out.device == dev, "out: bool/uint8 [>= n, 13527] rows")
+    if n:
+        nv.check(nv.lib().kz_bitmap_expand(bitmap.data_ptr(), bitmap.stride(0), nv.ptr(rows), n, out.data_ptr(), out.stride(0),
+                                           nv.stream_ptr(dev)), "kz_bitmap_expand")
+    return out
 
 
 def gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, last_value: torch.Tensor,
@@ -63,9 +110,10 @@ class _MaskedCategoricalEval(torch.autograd.Function):
         ent = torch.empty(n, dtype=torch.float32, device=dev)
         saved = torch.empty((n, 4), dtype=torch.float32, device=dev)
         actions = actions.contiguous().long()
-        nv.check(nv.lib().kz_eval_masked_fwd(logits.data_ptr(), int(logits.dtype == torch.bfloat16), logits.stride(0),
-                                             mask.data_ptr(), mask.stride(0), nv.ptr(mask_rows), actions.data_ptr(), n,
-                                             logp.data_ptr(), ent.data_ptr(), saved.data_ptr(), nv.stream_ptr(dev)),
+        fn = nv.lib().kz_eval_bitmap_fwd if is_bitmap(mask) else nv.lib().kz_eval_masked_fwd
+        nv.check(fn(logits.data_ptr(), int(logits.dtype == torch.bfloat16), logits.stride(0),
+                    mask.data_ptr(), mask.stride(0), nv.ptr(mask_rows), actions.data_ptr(), n,
+                    logp.data_ptr(), ent.data_ptr(), saved.data_ptr(), nv.stream_ptr(dev)),
                  "kz_eval_masked_fwd")
         ctx.save_for_backward(logits, mask, actions, saved)
         ctx.mask_rows = mask_rows
@@ -79,22 +127,26 @@ class _MaskedCategoricalEval(torch.autograd.Function):
         ldg = (nv.NUM_ACTIONS + 15) // 16 * 16
         store = torch.empty((n, ldg), dtype=logits.dtype, device=dev)  # 16-byte aligned rows; the kernel clears [0, A)
         store[:, nv.NUM_ACTIONS:].zero_()
-        nv.check(nv.lib().kz_eval_masked_bwd(logits.data_ptr(), int(logits.dtype == torch.bfloat16), logits.stride(0),
-                                             mask.data_ptr(), mask.stride(0), nv.ptr(ctx.mask_rows), actions.data_ptr(), n,
-                                             dlogp.contiguous().float().data_ptr(), dent.contiguous().float().data_ptr(),
-                                             saved.data_ptr(), store.data_ptr(), ldg, nv.stream_ptr(dev)),
-                 "kz_eval_masked_bwd")
+        args = (logits.data_ptr(), int(logits.dtype == torch.bfloat16), logits.stride(0),
+                mask.data_ptr(), mask.stride(0), nv.ptr(ctx.mask_rows), actions.data_ptr(), n,
+                dlogp.contiguous().float().data_ptr(), dent.contiguous().float().data_ptr(),
+                saved.data_ptr(), store.data_ptr(), ldg)
+        if is_bitmap(mask):
+            nv.check(nv.lib().kz_eval_bitmap_bwd(*args, None, nv.stream_ptr(dev)), "kz_eval_bitmap_bwd")
+        else:
+            nv.check(nv.lib().kz_eval_masked_bwd(*args, nv.stream_ptr(dev)), "kz_eval_masked_bwd")
         return store[:, : nv.NUM_ACTIONS], None, None, None
 
 
 def evaluate_masked(logits: torch.Tensor, mask: torch.Tensor, actions: torch.Tensor,
                     mask_rows: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """(log_prob of ``actions``, entropy) of the masked softmax over ``logits`` [B, 13527], differentiable w.r.t.
-    the logits.  ``mask`` is [B, 13527] (bool/uint8, any row stride) or, with ``mask_rows`` (int64 [B]), the whole
-    rollout mask storage indexed per row -- no minibatch gather of masks."""
+    the logits.  ``mask`` is [B, 13527] (bool/uint8, any row stride) -- or the engine's legal bitmap rows, int32
+    [B, 448] -- or, with ``mask_rows`` (int64 [B]), the whole rollout mask / bitmap storage indexed per row: no
+    minibatch gather of masks."""
     nv.require(logits.dim() == 2 and logits.shape[1] == nv.NUM_ACTIONS and logits.stride(1) == 1, "logits.dim() == 2 and logits.shape[1] == nv.NUM_ACTIONS and logits.stride(1) == 1")
     nv.require(logits.dtype in (torch.float32, torch.bfloat16), "logits.dtype in (torch.float32, torch.bfloat16)")
-    nv.require(mask.stride(-1) == 1 and mask.dtype in (torch.uint8, torch.bool) and mask.dim() == 2, "mask.stride(-1) == 1 and mask.dtype in (torch.uint8, torch.bool) and mask.dim() == 2")
+    _check_legal_rows(mask, "mask")
     if mask_rows is not None:
         mask_rows = mask_rows.contiguous().long()
     return _MaskedCategoricalEval.apply(logits, mask, actions, mask_rows)

@@ -86,7 +86,9 @@ class ParallelManager:
             "obs": b.obs[:T].transpose(0, 1).reshape(T * N, 46, 9, 9), "actions": b.actions.t().reshape(-1),
             "rewards": b.rewards.t().reshape(-1), "log_probs": b.log_probs.t().reshape(-1),
             "values": b.values.t().reshape(-1), "dones": b.dones.t().reshape(-1).bool(),
-            "legal_masks": b.masks[:T].transpose(0, 1).reshape(T * N, -1).bool()})
+            # worker-major order like the reference's per-worker batches: flat row of (n, t) is t * N + n
+            "legal_masks": b.legal_masks((torch.arange(T, device=b.device)[None, :] * N
+                                          + torch.arange(N, device=b.device)[:, None]).reshape(-1))})
         b.clear()
         added = experience_buffer.size() - before
         self.total_steps_collected += added

@@ -210,8 +210,8 @@ class StepManager:
 
 
 class VecStepManager:
-    """Batched rollout driver: for t in [0, T): obs[t], masks[t] -> agent.select_actions -> kz_step, which writes
-    reward/done and the next observation/mask straight into obs[t+1] / masks[t+1] of the RolloutBuffer.  The
+    """Batched rollout driver: for t in [0, T): obs[t], bitmaps[t] -> agent.select_actions -> kz_step_rollout, which
+    writes reward/done and the next observation / legal bitmap straight into obs[t+1] / bitmaps[t+1] of the RolloutBuffer.  The
     stored transition is the reference's (obs before the move, action, reward to the mover, log-prob, value,
     done, mask before the move; step_manager.py:272-301); finished games are reset inside the same launch and
     both colours' plies share one sequence per env, with no sign flips."""
@@ -227,24 +227,23 @@ class VecStepManager:
 
     def start(self) -> None:
         self.env.reset(refresh=False)
-        self.env.refresh(obs=self.buffer.obs[0], mask=self.buffer.masks[0])
+        self.env.legal_bitmap(self.buffer.bitmaps[0], obs=self.buffer.obs[0])
         self._started = True
 
     def collect(self) -> None:
-        """Fill the buffer with T steps of N games.  No host synchronisation inside the loop."""
+        """Fill the buffer with T steps of N games.  No host synchronisation inside the loop; the sampler writes the
+        action / log-prob rows and the engine writes reward / done / next observation / next legal bitmap straight
+        into the rollout storage."""
         if not self._started:
             self.start()
         b, env = self.buffer, self.env
         for t in range(b.T):
-            action, log_prob, value = self.agent.select_actions(b.obs[t], b.masks[t], is_training=True)
-            b.actions[t].copy_(action)
-            b.log_probs[t].copy_(log_prob)
+            _, _, value = self.agent.select_actions(b.obs[t], b.bitmaps[t], is_training=True,
+                                                    out=(b.actions[t], b.log_probs[t]))
             b.values[t].copy_(value)
-            out = env.step(b.actions[t], obs=b.obs[t + 1], mask=b.masks[t + 1])
-            b.rewards[t].copy_(out["reward"])
-            b.dones[t].copy_(out["done"])
+            out = env.step_rollout(b.actions[t], b.obs[t + 1], b.bitmaps[t + 1], reward=b.rewards[t], done=b.dones[t])
             w = out["winner"]
-            d = out["done"] != 0
+            d = b.dones[t] != 0
             self._stat += torch.stack([d.sum(), (d & (w == 0)).sum(), (d & (w == 1)).sum(), (d & (w < 0)).sum()])
 
     def finish(self) -> Dict[str, int]:

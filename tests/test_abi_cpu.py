@@ -28,7 +28,7 @@ def test_header_symbols_exported():
 
 def test_abi_version_and_layout():
     L = nv.lib()
-    assert L.kz_abi_version() == 1
+    assert L.kz_abi_version() == 2
     offs = (C.c_int64 * 3)()
     total = C.c_int64()
     assert L.kz_state_layout(65536, 500, offs, C.byref(total)) == 0
@@ -97,6 +97,13 @@ def test_invalid_arguments_are_rejected_before_any_device_work():
     assert L.kz_step(z, 4, 500, z, 1, z, 0, z, 0, z, z, z, z, z, z, z, 0, 0, 0, 1, z) == -1
     assert L.kz_step_compact(z, 4, 500, z, 1, z, z, z, z, z, z, z, z, 0, 0, 0, 1, z) == -1
     assert L.kz_expand(z, 4, 500, z, z, 0, z, 0, z) == -1
+    assert L.kz_step_rollout(z, 4, 500, z, 1, z, 0, z, 448, z, z, z, z, z, z, z, 0, 0, 0, 1, z) == -1
+    assert L.kz_legal_bitmap(z, 4, 500, z, 0, z, 448, z, z) == -1
+    assert L.kz_step_range(z, 4, 500, 0, 2, 0, z, 1, z, 0, z, 0, z, 0, z, z, z, z, z, z, z, 0, 0, 0, 1, z) == -1
+    assert L.kz_bitmap_expand(z, 448, z, 4, z, 13536, z) == -1
+    assert L.kz_sample_bitmap(z, 0, 13527, z, 448, 4, 0, 0, z, 1, z, z, 0, z) == -1
+    assert L.kz_eval_bitmap_fwd(z, 0, 13527, z, 448, z, z, 4, z, z, z, z) == -1
+    assert L.kz_eval_bitmap_bwd(z, 0, 13527, z, 448, z, z, 4, z, z, z, z, 13536, z, z) == -1
     assert L.kz_legal_mask(z, 4, 500, z, 0, z, z) == -1
     assert L.kz_observe(z, 4, 500, z, 0, z) == -1
     assert L.kz_piece_targets(z, 4, 500, z, z, z) in bad

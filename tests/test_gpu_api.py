@@ -179,9 +179,15 @@ def test_vectorised_rollout_and_update():
         drv.collect()
         stats = drv.finish()
         total_eps += stats["episodes"]
-        b = buf.get_batch()
+        b = buf.get_batch(expand_masks=True)
         assert b["obs"].shape == (T * N, 46, 9, 9) and b["legal_masks"].dtype == torch.bool
+        assert b["legal_bitmaps"].shape == (T * N, 448) and "legal_masks" not in buf.get_batch()
         assert bool(b["legal_masks"].gather(1, b["actions"][:, None]).all())
+        assert torch.equal(buf.masks_at(3), b["legal_masks"][3 * N:4 * N])
+        # the stored legal sets are the engine's: recompute the last slot's mask from the live games
+        if _ == 0:
+            env.refresh()
+            assert torch.equal(buf.masks_at(T).view(torch.uint8), env.mask)
         # stored observations are the engine's observation of the stored state: plane 42 = side to move
         assert bool(((b["obs"][:, 42, 0, 0] == 0) | (b["obs"][:, 42, 0, 0] == 1)).all())
         a_ref, r_ref = orc.gae(buf.rewards.cpu().numpy(), buf.values.cpu().numpy(), buf.dones.cpu().numpy(),

@@ -104,10 +104,59 @@ def test_golden_endgame_traces_replay(golden_dir):
     batch loaded from the fixture's SFENs: legal masks before every ply, successor boards / hands / side / move count,
     reward, done, reason, winner and the observation digest after it.  Games that ended early idle on a finished
     position (make_move then returns the terminal tuple again) and are no longer compared."""
-    from shogidrl_b200 import VecShogiEnv
-
     with np.load(os.path.join(golden_dir, "traces_endgame.npz")) as zf:
         z = {k: zf[k] for k in zf.files}
+    plies = _replay_sfen_traces(z)
+    assert plies == len(z["actions"]) and int((z["actions"] >= 12960).sum()) > 1000
+
+
+def test_golden_stalemate(golden_dir):
+    """Stalemate (no legal move, not in check) is a DRAW in the reference (shogi_game.py:431-435): reason 2, no winner,
+    reward 0.  Fixture from the imported reference (oracle/gen_golden_stalemate.py): the reference test-suite's
+    stalemate-at-load and stalemate-by-move positions, and 12 bare-king endgames whose random play ends in stalemate."""
+    from shogidrl_b200 import VecShogiEnv
+
+    with np.load(os.path.join(golden_dir, "traces_stalemate.npz")) as zf:
+        z = {k: zf[k] for k in zf.files}
+    dev = torch.device("cuda:0")
+    env = VecShogiEnv(2, max_moves_per_game=500, device=dev, auto_reset=False)
+    env.load_sfens([str(z["kat_load_sfen"]), str(z["kat_move_sfen"])])
+    _, _, m = [x.cpu().numpy() for x in env.export()]
+    assert (m[0, 3], m[0, 4]) == (2, -1) == (int(z["kat_load_reason"]), int(z["kat_load_winner"]))  # over at load: stalemate
+    assert int(env.legal_count[0]) == 0 and int(env.mask[0].sum()) == 0
+    assert np.array_equal(env.obs[0].cpu().numpy(), z["kat_load_obs"])
+    assert m[1, 3] == 0 and np.array_equal(np.nonzero(env.mask[1].cpu().numpy())[0], z["kat_move_legal"].astype(np.int64))
+    out = env.step(torch.as_tensor([0, int(z["kat_move_action"])], dtype=torch.int64, device=dev))
+    assert (float(out["reward"][1]), int(out["done"][1]), int(out["reason"][1]), int(out["winner"][1])) == (0.0, 1, 2, -1)
+    assert np.array_equal(out["obs"][1].cpu().numpy(), z["kat_move_obs"]) and int(out["legal_count"][1]) == 0
+    # make_move on the game that was already over returns its terminal tuple again (shogi_game.py:589-593)
+    assert (float(out["reward"][0]), int(out["done"][0]), int(out["reason"][0]), int(out["winner"][0])) == (0.0, 1, 2, -1)
+    plies = _replay_sfen_traces(z)
+    assert plies == len(z["actions"])
+    ends = np.cumsum(z["T"]) - 1
+    assert np.all(z["reasons"][ends] == 2) and np.all(z["winners"][ends] == -1) and np.all(z["rewards"][ends] == 0)
+    # the same through auto-reset: the finished games restart from the initial position in the same launch
+    n = len(z["sfens"])
+    env = VecShogiEnv(n, max_moves_per_game=500, device=dev, auto_reset=True)
+    env.load_sfens([str(s) for s in z["sfens"]])
+    starts = np.concatenate([[0], np.cumsum(z["T"])])[:-1]
+    env.refresh(random_actions=True)  # games whose trace has ended play on from the start position with random legal moves
+    for t in range(int(z["T"].max())):
+        live = np.nonzero(z["T"] > t)[0]
+        acts = env.next_actions.clone()
+        acts[torch.as_tensor(live, device=dev)] = torch.as_tensor(z["actions"][starts[live] + t].astype(np.int64), device=dev)
+        out = env.step(acts, random_actions=True)
+        last = live[z["T"][live] == t + 1]
+        if len(last):
+            li = torch.as_tensor(last, device=dev)
+            assert bool((out["done"][li] == 1).all()) and bool((out["reason"][li] == 2).all())
+            assert bool((out["winner"][li] == -1).all()) and bool((out["reward"][li] == 0).all())
+            assert bool((out["legal_count"][li] == 30).all())  # reset to the start position
+
+
+def _replay_sfen_traces(z):
+    from shogidrl_b200 import VecShogiEnv
+
     dev = torch.device("cuda:0")
     n = len(z["sfens"])
     starts = np.concatenate([[0], np.cumsum(z["T"])])[:-1]
@@ -140,7 +189,7 @@ def test_golden_endgame_traces_replay(golden_dir):
             assert _digest(obs[e]) == int(z["digests"][i]), (e, t)
         assert int(env.errors()[torch.as_tensor(live, device=dev)].abs().sum()) == 0
         plies += len(live)
-    assert plies == len(z["actions"]) and int((z["actions"] >= 12960).sum()) > 1000
+    return plies
 
 
 def test_golden_full_observations(traces):
@@ -551,3 +600,45 @@ def test_split_pipeline_equals_fused_step(n, T):
         finished += int(oa["done"].sum())
     assert finished > 0 and all(torch.equal(x, y) for x, y in zip(a.export(), b.export()))
     assert int(a.errors().abs().sum()) == 0 and int(b.errors().abs().sum()) == 0
+
+
+@pytest.mark.parametrize("n,T", [(4096, 90), (8, 70)])
+def test_row_writer_variants_agree(n, T):
+    """kz_step composes 32-byte aligned, padded mask rows once from the legal bitmap, and writes exactly-13,527-byte rows
+    byte by byte; the rollout form (kz_step_rollout) leaves the bitmap itself; a batch may be stepped as concurrent
+    ranges of games (kz_step_range, ``step_streams``).  Triplet batches must produce identical masks, observations,
+    scalars and next actions every step, across auto-resets."""
+    from shogidrl_b200 import VecShogiEnv, rl
+
+    dev = torch.device("cuda:0")
+    envs = [VecShogiEnv(n, max_moves_per_game=60, device=dev, seed=11, step_streams=k) for k in (1, 2 if n >= 64 else 1, 2 if n >= 64 else 1)]
+    assert envs[2].step_streams == (2 if n >= 64 else 1)
+    acts = [[torch.zeros(n, dtype=torch.int64, device=dev) for _ in range(2)] for _ in range(3)]
+    for e, a in zip(envs, acts):
+        e.refresh(random_actions=True, next_out=a[0])
+    contiguous = torch.zeros((n, 13527), dtype=torch.uint8, device=dev)
+    bitmap = torch.zeros((n, 448), dtype=torch.int32, device=dev)
+    obs_r = torch.zeros((n, 46, 9, 9), dtype=torch.float32, device=dev)
+    finished = 0
+    for t in range(T):
+        for e in envs[:1]:
+            e.obs.fill_(-3.0); e._mask_store.fill_(5)
+        contiguous.fill_(9); envs[1].obs.fill_(7.0); obs_r.fill_(-1.0); bitmap.fill_(-1)
+        o0 = envs[0].step(acts[0][t & 1], random_actions=True, next_out=acts[0][(t + 1) & 1])            # composed once
+        o1 = envs[1].step(acts[1][t & 1], mask=contiguous, random_actions=True, next_out=acts[1][(t + 1) & 1])  # byte rows
+        o2 = envs[2].step_rollout(acts[2][t & 1], obs_r, bitmap, random_actions=True, next_out=acts[2][(t + 1) & 1])
+        assert torch.equal(envs[0].mask, contiguous), t
+        assert torch.equal(envs[0].obs, envs[1].obs) and torch.equal(envs[0].obs, obs_r), t
+        assert torch.equal(rl.bitmap_to_mask(bitmap).view(torch.uint8), contiguous), t
+        assert bool((envs[0]._mask_store[:, 13527:] == 0).all())
+        for k in ("reward", "done", "reason", "winner", "ep_len", "legal_count"):
+            assert torch.equal(o0[k], o1[k]) and torch.equal(o0[k], o2[k]), (t, k)
+        assert torch.equal(acts[0][(t + 1) & 1], acts[1][(t + 1) & 1]) and torch.equal(acts[0][(t + 1) & 1], acts[2][(t + 1) & 1])
+        finished += int(o0["done"].sum())
+    assert finished > 0
+    for e in envs:
+        assert int(e.errors().abs().sum()) == 0
+    assert all(torch.equal(x, y) for x, y in zip(envs[0].export(), envs[2].export()))
+    b2 = torch.zeros_like(bitmap)
+    envs[0].legal_bitmap(b2)
+    assert torch.equal(b2, bitmap)

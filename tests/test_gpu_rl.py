@@ -393,3 +393,98 @@ def test_fused_clip_adam_rejects_what_it_cannot_mirror():
     assert not rl.adam_clip_applicable(torch.optim.AdamW(p, lr=1e-3))
     assert not rl.adam_clip_applicable(torch.optim.SGD(p, lr=1e-3))
     assert not rl.adam_clip_applicable(torch.optim.Adam([{"params": p}, {"params": [torch.nn.Parameter(torch.zeros(2, device="cuda"))]}], lr=1e-3))
+
+
+# ------------------------------------------------------------------------------------------------
+# legal sets as the engine's 13,527-bit bitmap rows (kz_sample_bitmap, kz_eval_bitmap_*, kz_bitmap_expand)
+def _pack_bitmap(mask):
+    """bool [n, 13527] -> int32 [n, 448] (bit i of a row = action i), on the mask's device."""
+    n = mask.shape[0]
+    padded = torch.zeros((n, 448 * 32), dtype=torch.int64, device=mask.device)
+    padded[:, :A] = mask.long()
+    words = (padded.view(n, 448, 32) << torch.arange(32, device=mask.device)).sum(-1)
+    return (words & 0xFFFFFFFF).to(torch.int64).where(words < 2 ** 31, words - 2 ** 32).to(torch.int32).contiguous()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("legal_p", [0.004, 0.3])
+def test_bitmap_rows_equal_byte_mask_rows(dtype, legal_p):
+    """The bitmap entry points return, bit for bit, what the byte-mask entry points return for 16-byte aligned rows of
+    the same legal sets: sampled actions, arg-max actions, log-probs, entropies, dlogits and the bias gradient; and
+    both stay within 1e-5 of the fp32 torch formulation."""
+    from shogidrl_b200 import rl, nn_ops
+    dev = torch.device("cuda:0")
+    n = 777
+    logits, mask = _random_case(n, dev, seed=5, legal_p=legal_p)
+    mask[3] = False  # an all-illegal row (uniform fallback) in both encodings
+    mask[5] = False; mask[5, A - 1] = True  # the last action only
+    logits = logits.to(dtype)
+    store = torch.zeros((n, 13536), dtype=torch.uint8, device=dev)  # aligned rows, as the engine writes them
+    store[:, :A] = mask
+    bytes_ = store[:, :A]
+    bm = _pack_bitmap(mask)
+    assert torch.equal(rl.bitmap_to_mask(bm), mask)
+    rows = torch.randperm(n, device=dev)[:100]
+    assert torch.equal(rl.bitmap_to_mask(bm, rows), mask[rows])
+    odd = torch.zeros((n, A + 3), dtype=torch.bool, device=dev)[:, 1:A + 1]  # unaligned destination rows
+    assert torch.equal(rl.bitmap_to_mask(bm, out=odd), mask)
+    for det in (False, True):
+        a1, l1, e1 = rl.sample_masked(logits, bytes_, seed=9, offset=4, deterministic=det, want_entropy=True)
+        a2, l2, e2 = rl.sample_masked(logits, bm, seed=9, offset=4, deterministic=det, want_entropy=True)
+        assert torch.equal(a1, a2) and torch.equal(l1, l2) and torch.equal(e1, e2)
+    ok = mask.any(1)
+    assert bool(mask[ok].gather(1, a2[ok, None]).all())
+    # evaluation forward / backward
+    lg1 = logits.clone().requires_grad_(True)
+    lg2 = logits.clone().requires_grad_(True)
+    act = a2.clone()
+    lp1, en1 = rl.evaluate_masked(lg1, bytes_, act)
+    lp2, en2 = rl.evaluate_masked(lg2, bm, act)
+    assert torch.equal(lp1, lp2) and torch.equal(en1, en2)
+    w = torch.randn(n, device=dev)
+    (lp1 * w).sum().backward(retain_graph=True); (en1 * w * 0.3).sum().backward()
+    (lp2 * w).sum().backward(retain_graph=True); (en2 * w * 0.3).sum().backward()
+    assert torch.equal(lg1.grad, lg2.grad)
+    if dtype == torch.float32:
+        ref = logits.clone().requires_grad_(True)
+        probs, dist = _torch_reference(ref, mask)
+        assert torch.allclose(lp2, dist.log_prob(act), rtol=1e-5, atol=1e-6)
+        assert torch.allclose(en2, dist.entropy(), rtol=1e-5, atol=1e-5)
+    # through row indices into a larger storage, as the PPO update reads the rollout buffer
+    perm = torch.randperm(n, device=dev)
+    lp3, en3 = rl.evaluate_masked(logits[perm].contiguous(), bm, act[perm], mask_rows=perm)
+    assert torch.equal(lp3, lp2[perm]) and torch.equal(en3, en2[perm])
+
+
+def test_policy_head_bias_gradient_is_deterministic_and_matches_column_sums():
+    """kz_eval_*_bwd accumulates the policy head's bias gradient in Q20.44 fixed point: identical bits run to run
+    (an fp32 atomicAdd is not), equal for the byte-mask and bitmap forms, and equal to the column sums of dlogits."""
+    from shogidrl_b200 import nn_ops
+    dev = torch.device("cuda:0")
+    n, k = 4096, 64
+    g = torch.Generator(device="cpu").manual_seed(2)
+    h = torch.randn(n, k, generator=g).to(dev).bfloat16()
+    lin = torch.nn.Linear(k, A).to(dev)
+    _, mask = _random_case(n, dev, seed=8, legal_p=0.01)
+    store = torch.zeros((n, 13536), dtype=torch.uint8, device=dev)
+    store[:, :A] = mask
+    bm = _pack_bitmap(mask)
+    act = torch.multinomial(mask.float(), 1).squeeze(1)
+    wl = torch.randn(n, device=dev)
+    grads = []
+    for legal in (store[:, :A], bm, store[:, :A], bm):
+        lin.zero_grad()
+        lp, en = nn_ops.policy_head_evaluate(h, lin, legal, act)
+        ((lp * wl).sum() + 0.01 * en.sum()).backward()
+        grads.append((lin.bias.grad.clone(), lin.weight.grad.clone()))
+    for b, w in grads[1:]:
+        assert torch.equal(b, grads[0][0]) and torch.equal(w, grads[0][1])
+    # against the dense formulation in fp32
+    lin32 = torch.nn.Linear(k, A).to(dev)
+    lin32.load_state_dict(lin.state_dict())
+    logits = torch.nn.functional.linear(h.float(), lin32.weight.bfloat16().float(), lin32.bias.bfloat16().float())
+    logits = logits.detach().bfloat16().float().requires_grad_(True)
+    probs, dist = _torch_reference(logits, mask)
+    ((dist.log_prob(act) * wl).sum() + 0.01 * dist.entropy().sum()).backward()
+    ref_db = logits.grad.sum(0)
+    assert torch.allclose(grads[0][0], ref_db, rtol=2e-3, atol=2e-3 * float(ref_db.abs().max()))

@@ -153,3 +153,44 @@ def test_endgame_traces_bit_exact(golden_dir):
             assert _digest(g.observation()) == int(z["digests"][i]), (gi, t)
         base += int(z["T"][gi])
     assert base == len(z["actions"]) and int((z["actions"] >= 12960).sum()) > 500
+
+
+def test_stalemate_fixture_bit_exact(golden_dir):
+    """Stalemate -- no legal move, not in check: a DRAW in the reference (shogi_game.py:431-435) -- from the fixture
+    oracle/gen_golden_stalemate.py produced with the imported reference: the reference test-suite's two positions
+    (stalemate at load, stalemate by a move) and 12 random bare-king endgames that end in stalemate."""
+    with np.load(os.path.join(golden_dir, "traces_stalemate.npz")) as zf:
+        z = {k: zf[k] for k in zf.files}
+    # known answers
+    g = orc.OracleGame.from_sfen(str(z["kat_load_sfen"]))
+    m = g.meta
+    assert (m[3], m[5], m[4]) == (int(z["kat_load_game_over"]), int(z["kat_load_reason"]), int(z["kat_load_winner"])) == (1, 2, -1)
+    assert len(g.legal_indices()) == int(z["kat_load_legal_n"]) == 0
+    assert np.array_equal(g.observation(), z["kat_load_obs"])
+    g = orc.OracleGame.from_sfen(str(z["kat_move_sfen"]))
+    assert np.array_equal(g.legal_indices(), z["kat_move_legal"].astype(np.int32))
+    reward, done, reason, winner = g.make_move(int(z["kat_move_action"]))
+    assert (reward, done, reason, winner) == (0.0, True, 2, -1)
+    assert (reward, done, reason, winner) == (float(z["kat_move_reward"]), bool(z["kat_move_done"]), int(z["kat_move_reason"]),
+                                              int(z["kat_move_winner"]))
+    assert np.array_equal(g.observation(), z["kat_move_obs"]) and len(g.legal_indices()) == int(z["kat_move_legal_after"])
+    # games that end in stalemate
+    base = 0
+    for gi, sfen in enumerate(z["sfens"]):
+        g = orc.OracleGame.from_sfen(str(sfen))
+        env = int(z["envs"][gi])
+        for t in range(int(z["T"][gi])):
+            i = base + t
+            want = z["legal"][z["legal_off"][i]:z["legal_off"][i + 1]].astype(np.int32)
+            assert np.array_equal(g.legal_indices(), want), (gi, t, sfen)
+            a = g.pick_action(int(z["seed"]), env, t)
+            assert a == int(z["actions"][i]), (gi, t)
+            reward, done, reason, winner = g.make_move(a)
+            b, h, m = g.export()
+            assert np.array_equal(b, z["boards"][i]) and np.array_equal(h, z["hands"][i]), (gi, t)
+            assert (reward, done, reason, winner) == (float(z["rewards"][i]), bool(z["dones"][i]), int(z["reasons"][i]),
+                                                      int(z["winners"][i])), (gi, t)
+            assert _digest(g.observation()) == int(z["digests"][i]), (gi, t)
+        base += int(z["T"][gi])
+        assert (reward, done, reason, winner) == (0.0, True, 2, -1), sfen  # every game ends in a stalemate draw
+    assert base == len(z["actions"]) and len(z["sfens"]) >= 8
