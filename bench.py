@@ -108,7 +108,7 @@ class ClockSampler:
 def cpu_baseline_sample(threads: int, seconds_budget: float = 20.0):
     """The oracle port timed on the host cores on a bounded sample of the same workload."""
     from oracle import oracle as orc
-    n = 256 * threads
+    n = GAMES_PER_THREAD * threads
     batch = orc.OracleBatch(n, MAX_MOVES, SEED, threads)
     batch.run(8)  # warm caches / threads
     t0 = time.perf_counter()
@@ -124,6 +124,31 @@ def cpu_baseline_sample(threads: int, seconds_budget: float = 20.0):
                       f"legal moves + mask + make_move + observation per ply, {dt:.1f} s, C oracle (oracle/keisei_oracle.c)"}
 
 
+def real_reference_ppo_sample(threads: int, timesteps: int = 256, epochs: int = 10, minibatch: int = 64):
+    """BASELINE.md section 3.2 on this box: the unmodified reference's sequential PPO loop (baseline/ref_ppo_loop.py over
+    baseline/_ref), one process with `threads` torch threads, one epoch of `timesteps` steps.  None without the install."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "keisei")):
+        return None
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1", WANDB_DISABLED="true", WANDB_MODE="disabled")
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "baseline", "ref_ppo_loop.py"), ref_dir, str(timesteps),
+                              str(epochs), str(minibatch), str(threads)], capture_output=True, text=True, env=env, timeout=600)
+        r = json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as ex:
+        return {"unavailable": "baseline/_ref is present but the reference PPO loop did not run here: "
+                               + (str(ex) + " " + (locals().get("out").stderr[-300:] if locals().get("out") else "")).replace("\n", " | ")}
+    return {"value": r["samples_per_s"], "unit": "samples/s", "cores": threads, "kind": "reference",
+            "rollout_samples_per_s": timesteps / r["collect_s"], "update_samples_per_s": timesteps / r["update_s"],
+            "sample": f"1 epoch of {timesteps} timesteps (reference default 2048), minibatch {minibatch}, ppo_epochs {epochs}: keisei "
+                      f"ShogiGame + PolicyOutputMapper + PPOAgent.select_action / learn + ExperienceBuffer + ActorCritic(46, 13527) "
+                      f"from baseline/_ref on the CPU, one process, {threads} torch threads (collect {r['collect_s']:.1f} s, "
+                      f"update {r['update_s']:.1f} s)"}
+
+
+GAMES_PER_THREAD = 256  # both CPU legs (cpu_baseline of the product line, --impl reference) step this many games per host thread
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is pure Python and
     cannot travel to the GPU box) on all host threads.  One step = one env step of every game of the batch."""
@@ -132,7 +157,7 @@ def run_reference(args):
         return 0
     from oracle import oracle as orc
     threads = os.cpu_count() or 1
-    n = 64 * threads
+    n = GAMES_PER_THREAD * threads
     batch = orc.OracleBatch(n, MAX_MOVES, SEED, threads)
     batch.run(256)  # untimed pre-roll: spread the games over the phases of play
     for _ in range(args.warmup):
@@ -147,38 +172,91 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"random-legal self-play, {n} games per step on {threads} host threads (bounded sample of "
-                               f"BASELINE config 2: 65,536 games/GPU), max_moves {MAX_MOVES}, auto-reset, 256-ply pre-roll",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "threads": threads,
+        "config": {"workload": f"random-legal self-play, {n} games per step = {GAMES_PER_THREAD} per host thread x {threads} "
+                               f"threads (bounded sample of BASELINE config 2: 65,536 games/GPU; the CPU rate does not depend "
+                               f"on the batch size), max_moves {MAX_MOVES}, auto-reset, 256-ply pre-roll",
                    "mean_ply": plies / max(1, args.steps)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{n} games x {args.steps} timed plies, C oracle port of keisei.shogi (pure-Python reference "
-                                   "cannot run on the GPU box)"},
+                         "sample": f"{n} games x {args.steps} timed plies, C oracle port of keisei.shogi (the pure-Python "
+                                   "reference is timed separately: cpu_baseline_reference)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    ref = real_reference_sample(threads)
+    if ref is not None:
+        line["cpu_baseline_reference"] = ref
+    if not args.no_ppo:
+        # the second half of BASELINE.json's metric on the host: same minibatch size as the product arm states
+        line["ppo"] = measure_reference_ppo(args.ppo_minibatch, args.ppo_minibatch, args.ppo_epochs, 1, 0, threads)
+        line["ppo_reference_defaults"] = measure_reference_ppo(args.ref_ppo_steps, 64, args.ppo_epochs, 1, 0, threads)
+        rp = real_reference_ppo_sample(threads, epochs=args.ppo_epochs)
+        if rp is not None:
+            line["ppo_cpu_baseline_reference"] = rp
     emit(line)
     return 0
 
 
-def run_reference_ppo(args):
-    """--impl reference --workload ppo: the reference's sequential CPU trainer restated -- one game, batch-1
-    select_action (masked softmax + Categorical sample, ppo_agent.py:134-223), ExperienceBuffer GAE
-    (experience_buffer.py:99-145), then PPOAgent.learn (ppo_agent.py:243-460: ppo_epochs x minibatches of 64, clipped
-    surrogate + value MSE + entropy, clip_grad_norm_ 0.5, Adam) -- on the oracle engine and the default CNN
-    (neural_network.py:10-29) in plain fp32 PyTorch on all host threads.  One step = one epoch of `--ref-ppo-steps`
-    timesteps (a bounded sample of the reference's steps_per_epoch = 2048); value = timesteps per second."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return 0
+def real_reference_sample(threads: int, seconds: float = 30.0):
+    """The UNMODIFIED Python reference (keisei.shogi.ShogiGame + PolicyOutputMapper from baseline/_ref, installed with
+    `pip install --no-deps --target baseline/_ref`), BASELINE.md section 3.1 loop -- get_legal_moves, get_legal_mask,
+    make_move with the config-1 action rule -- in `threads` processes for `seconds` of wall time.  None when the install
+    is not on this box (it is git-ignored and only travels with an untracked copy of the tree)."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "keisei")):
+        return None
+    code = (
+        "import sys, time, random\n"
+        f"sys.path.insert(0, {ref_dir!r})\n"
+        "import torch; torch.set_num_threads(1)\n"
+        "from keisei.shogi import ShogiGame\n"
+        "from keisei.utils import PolicyOutputMapper\n"
+        "seed, budget = int(sys.argv[1]), float(sys.argv[2])\n"
+        "rng = random.Random(seed); mapper = PolicyOutputMapper(); g = ShogiGame(max_moves_per_game=500)\n"
+        "dev = torch.device('cpu'); n = 0; t0 = time.perf_counter()\n"
+        "while time.perf_counter() - t0 < budget:\n"
+        "    lm = g.get_legal_moves()\n"
+        "    if not lm or g.game_over:\n"
+        "        g.reset(); continue\n"
+        "    mapper.get_legal_mask(lm, dev)\n"
+        "    idx = sorted(mapper.shogi_move_to_policy_index(m) for m in lm)\n"
+        "    g.make_move(mapper.policy_index_to_shogi_move(idx[rng.randrange(len(idx))]))\n"
+        "    n += 1\n"
+        "print(n, time.perf_counter() - t0)\n")
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1", WANDB_DISABLED="true", WANDB_MODE="disabled")
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(100 + i), str(seconds)], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True, env=env) for i in range(threads)]
+    steps, ok, err = 0, 0, ""
+    for p in procs:
+        try:
+            out, e = p.communicate(timeout=seconds + 240)
+            a, _ = out.split()
+            steps += int(a); ok += 1
+        except Exception as ex:  # import failure on this box, timeout, ...
+            p.kill()
+            err = (locals().get("e") or str(ex))[-300:]
+    wall = time.perf_counter() - t0
+    if ok == 0:
+        return {"unavailable": "baseline/_ref is present but the reference did not run here: " + err.strip().replace("\n", " | ")}
+    return {"value": steps / seconds, "unit": UNIT, "cores": ok, "kind": "reference", "per_core": steps / seconds / ok,
+            "sample": f"{ok} processes x {seconds:.0f} s of keisei.shogi.ShogiGame from baseline/_ref (get_legal_moves + "
+                      f"get_legal_mask + make_move, uniform-random legal play from the start position, max_moves 500), "
+                      f"{steps} plies, {wall:.0f} s wall incl. imports"}
+
+
+def measure_reference_ppo(S, MB, EPOCHS, steps, warm, threads):
+    """The reference's sequential CPU trainer restated -- one game, batch-1 select_action (masked softmax + Categorical
+    sample, ppo_agent.py:134-223), ExperienceBuffer GAE (experience_buffer.py:99-145), then PPOAgent.learn
+    (ppo_agent.py:243-460: ppo_epochs x minibatches of MB, clipped surrogate + value MSE + entropy, clip_grad_norm_ 0.5,
+    Adam) -- on the oracle engine and the default CNN (neural_network.py:10-29) in plain fp32 PyTorch on all host threads.
+    One step = one epoch of S timesteps; value = timesteps per second."""
     import numpy as np
     import torch
     import torch.nn as nn
     from oracle import oracle as orc
-    threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     torch.manual_seed(SEED)
-    S, MB, EPOCHS = args.ref_ppo_steps, 64, args.ppo_epochs
     gamma, lam, clip_eps, cv, ce = 0.99, 0.95, 0.2, 0.5, 0.01
 
     class Net(nn.Module):  # keisei/core/neural_network.py:10-29
@@ -200,8 +278,6 @@ def run_reference_ppo(args):
     opt = torch.optim.Adam(model.parameters(), lr=3e-4)
     game = orc.OracleGame(MAX_MOVES)
     shuffle_rng = np.random.default_rng(SEED)
-    steps = max(1, min(args.steps, 8))
-    warm = min(args.warmup, 1)
 
     def epoch():
         obs = np.zeros((S, 46, 9, 9), np.float32); masks = np.zeros((S, 13527), np.uint8)
@@ -249,15 +325,30 @@ def run_reference_ppo(args):
     roll = sum(epoch() for _ in range(steps))
     dt = time.perf_counter() - t0
     value = S * steps / dt
-    sample = (f"{steps} epochs x {S} timesteps of one game (reference default: 2048), minibatch {MB}, ppo_epochs {EPOCHS}, "
+    sample = (f"{steps} epoch(s) x {S} timesteps of one game (reference default: 2048), minibatch {MB}, ppo_epochs {EPOCHS}, "
               f"C oracle engine + fp32 PyTorch CPU model on {threads} threads (the pure-Python reference cannot run on the GPU box)")
-    emit({"impl": "reference", "metric": "PPO self-play samples/sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
-          "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
-          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-          "config": {"workload": "BASELINE config 3 on the host: PPO self-play, cnn policy-value net, sequential trainer; " + sample,
-                     "rollout_samples_per_s": S * steps / roll, "update_samples_per_s": S * steps / max(1e-9, dt - roll)},
-          "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
-          "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+    return {"metric": "PPO self-play samples/sec", "value": value, "unit": "samples/s", "steps": steps, "warmup": warm,
+            "ms_per_step": 1e3 * dt / steps, "dtype": "f32", "threads": threads, "minibatch": MB, "timesteps_per_epoch": S,
+            "ppo_epochs": EPOCHS, "rollout_samples_per_s": S * steps / roll,
+            "update_samples_per_s": S * steps / max(1e-9, dt - roll), "kind": "port", "sample": sample}
+
+
+def run_reference_ppo(args):
+    """--impl reference --workload ppo: the PPO arm on the host as its own line."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    S = args.ref_ppo_steps
+    MB = min(args.ppo_minibatch, S) if args.ref_same_minibatch else 64
+    r = measure_reference_ppo(S, MB, args.ppo_epochs, max(1, min(args.steps, 8)), min(args.warmup, 1), threads)
+    emit({"impl": "reference", "metric": r["metric"], "value": r["value"], "unit": r["unit"], "n_gpus": args.gpus,
+          "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "threads": threads,
+          "config": {"workload": "BASELINE config 3 on the host: PPO self-play, cnn policy-value net, sequential trainer; " + r["sample"],
+                     "rollout_samples_per_s": r["rollout_samples_per_s"], "update_samples_per_s": r["update_samples_per_s"]},
+          "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": threads, "kind": "port", "sample": r["sample"]},
+          "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
     return 0
 
 
@@ -393,7 +484,7 @@ def run_product(args):
         return obs_buf[i % SLOTS][g * ng:(g + 1) * ng], mask_buf[i % SLOTS][g * ng:(g + 1) * ng, :13527]
 
     pipe.prime(random_actions=True)
-    for i in range(min(args.preroll, 128) + 3):                            # mid-game positions, pipeline warm
+    for i in range(args.preroll + args.warmup):                            # the same pre-roll as the device-timed leg: steady-state mix
         for g in range(G):
             pipe.h_actions[g].copy_(pipe.wait(g)[0])
             pipe.submit(g, *views(i, g), random_actions=True)
@@ -410,6 +501,12 @@ def run_product(args):
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
     errs += sum(int((e.errors() != 0).sum()) for e in pipe.envs)
+    e2e_mean_ply = float(torch.cat([e.export()[2][:, 1].float() for e in pipe.envs]).mean())
+    del pipe, obs_buf, mask_buf
+    torch.cuda.empty_cache()
+    ppo = None
+    if not args.no_ppo:
+        ppo = measure_ppo(args, dev, world, rank, barrier)
 
     if world > 1:
         t = torch.tensor([ms_total, e2e_ms, kernel_ms, serial_ms, full_ms], device=dev, dtype=torch.float64)
@@ -424,14 +521,17 @@ def run_product(args):
         bytes_per_launch = algorithmic_bytes_per_step(mean_ply) * n
         achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
         peak, peak_src = measured_peak_gbs()
-        traffic = None
-        try:
+        traffic, traffic_src = None, None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel (profiles/)
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                 tj = json.load(f)
                 if int(tj.get("envs", 0)) == n:
                     traffic = tj["dram_bytes_per_launch"]
+                    traffic_src = f"profiles/traffic.json: {tj.get('source', 'ncu --set full')} (kernel sources {tj.get('src_sha', '?')})"
         except Exception:
             pass
+        from shogidrl_b200 import _native as nv
+        build = nv.build_info()
         line = {
             "metric": METRIC, "value": world * n * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -444,29 +544,170 @@ def run_product(args):
                        "l2": "each step writes 1.86 GB of fresh obs+mask rows per GPU (2-slot ring), far above the 126 MB L2",
                        "algorithmic_bytes_per_env_step": algorithmic_bytes_per_step(mean_ply), "env_error_flags": errs},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "kz_step_kernel", "kernel_ms": kernel_ms, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "kz_step_kernel", "kernel_ms": kernel_ms,
+                         "peak_source": peak_src,
                          "achieved_implementation_bytes": implementation_bytes_per_step() * n / (kernel_ms * 1e-3) / 1e9,
                          "frac_implementation_bytes": implementation_bytes_per_step() * n / (kernel_ms * 1e-3) / 1e9 / peak},
             "e2e": {"value": world * n * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * n,
-                    "d2h_bytes_per_step": 15 * n, "steps": e2e_steps,
+                    "d2h_bytes_per_step": 15 * n, "steps": e2e_steps, "preroll_steps": args.preroll, "mean_ply": e2e_mean_ply,
                     "serial_value": world * n * e2e_steps / (serial_ms * 1e-3),
-                    "all_outputs_to_host_value": world * n * full_steps / (full_ms * 1e-3),
-                    "all_outputs_d2h_bytes_per_step": full_d2h,
-                    "note": "HostPipelinedEnv (2 groups, 2 streams): actions from pinned host memory, reward/done/reason/winner/"
-                            "next-action read back to pinned host memory every step, host waits for each group's results before "
-                            "submitting its next actions; obs/mask stay in HBM for the policy tower; serial_value = the same "
-                            "through one VecShogiEnv with copy -> kernel -> copy -> synchronise in sequence; all_outputs_to_host_value = the "
-                            "serial path when the observations and legal masks are ALSO copied to pinned host memory every "
-                            "step (1.86 GB per 65,536 games: PCIe-bound; only a caller with its policy network off the GPU "
-                            "needs that)"},
+                    "note": "HostPipelinedEnv (2 groups, 2 streams), same pre-roll and position mix as `value`: actions from "
+                            "pinned host memory, reward/done/reason/winner/next-action read back to pinned host memory every "
+                            "step, host waits for each group's results before submitting its next actions; obs/mask stay in "
+                            "HBM for the policy tower; it can exceed `value` because the two groups run ahead of each other "
+                            "(one group's CTAs fill the SMs the other's draining grid leaves idle); serial_value = the same "
+                            "through one VecShogiEnv with copy -> kernel -> copy -> synchronise in sequence"},
+            # what a caller of the reference's scalar API (observation + mask as host arrays) would see: PCIe-bound
+            "e2e_host_outputs": {"value": world * n * full_steps / (full_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * n,
+                                 "d2h_bytes_per_step": full_d2h, "steps": full_steps,
+                                 "note": "the serial path when the 46x9x9 observations and 13,527-byte legal masks are ALSO "
+                                         "copied to pinned host memory every step (1.86 GB per 65,536 games); only a caller "
+                                         "that keeps its policy network off the GPU needs that"},
+            "build": build,
             "gpu_launches": args.steps,
             "clocks": clocks,
         }
+        if ppo is not None:
+            line["ppo"] = ppo
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_sample(os.cpu_count() or 1)
+            threads = os.cpu_count() or 1
+            line["cpu_baseline"] = cpu_baseline_sample(threads)
+            ref = real_reference_sample(threads)  # the unmodified Python reference, when baseline/_ref travelled here
+            if ref is not None:
+                line["cpu_baseline_reference"] = ref
+            if ppo is not None:
+                rp = real_reference_ppo_sample(threads, epochs=args.ppo_epochs)
+                if rp is not None:
+                    ppo["cpu_baseline_reference"] = rp
         emit(line)
+    finish_process_group(world)
+    return 0
+
+
+def cfg5_positions(n: int):
+    """BASELINE config 5's start mix for n games: [hirate | drops-heavy endgames | 4-ply-cycle scripts], a third each.  The
+    endgames are the fixed list of 128 reference-validated SFENs in tests/golden/traces_endgame.npz (two kings, a few
+    pieces, full hands), tiled; the cycle script is the reference test-suite's sennichite position
+    (tests/shogi/test_shogi_game_core_logic.py:1126-1179).  -> boards, hands, sides, move_counts, (n_hirate, n_endgame, n_cycle)"""
+    import numpy as np
+    from shogidrl_b200.shogi.sfen import pack_sfen
+    n_e = n_c = n // 3
+    n_h = n - n_e - n_c
+    with np.load(os.path.join(ROOT, "tests", "golden", "traces_endgame.npz")) as z:
+        eg = [pack_sfen(str(x)) for x in z["sfens"]]
+    hirate = pack_sfen("lnsgkgsnl/1r5b1/ppppppppp/9/9/9/PPPPPPPPP/1B5R1/LNSGKGSNL b - 1")
+    cyc = pack_sfen("4k4/9/9/9/9/R8/9/9/4K4 b - 1")
+    idx = np.arange(n_e) % len(eg)
+    boards = np.concatenate([np.tile(hirate[0], (n_h, 1)), np.stack([p[0] for p in eg])[idx], np.tile(cyc[0], (n_c, 1))])
+    hands = np.concatenate([np.tile(hirate[1], (n_h, 1)), np.stack([p[1] for p in eg])[idx], np.tile(cyc[1], (n_c, 1))])
+    sides = np.concatenate([np.zeros(n_h, np.uint8), np.asarray([p[2] for p in eg], np.uint8)[idx], np.zeros(n_c, np.uint8)])
+    return boards.astype(np.int8), hands.astype(np.uint8), sides, np.zeros(n, np.int32), (n_h, n_e, n_c)
+
+
+CYCLE_MOVES = [(5, 0, 5, 1, False), (0, 4, 0, 3, False), (5, 1, 5, 0, False), (0, 3, 0, 4, False)]
+
+
+def run_cfg5(args):
+    """--workload cfg5: BASELINE config 5, the long-game stress -- `--envs` games per GPU (262,144), max_moves 500 with
+    500-ply repetition tables, start mix of cfg5_positions; the scripted third plays the 4-ply rook / king cycle and must
+    end by sennichite on ply 13; every finished game restarts from hirate.  One step = kz_step over the whole batch (legal
+    mask + obs + step, as config 2).  Reports steps/s over K timed steps after the pre-roll, the termination-reason
+    histogram of every game finished since the start, and the history memory.  (The histogram is checked against the
+    oracle on 4,096 sampled games of the same full-size batch by tests/test_gpu_engine.py::test_config5_full_size.)"""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.destroy_process_group()
+        dist.init_process_group("nccl", device_id=dev)
+    from shogidrl_b200 import VecShogiEnv, MASK_PAD_STRIDE
+    from shogidrl_b200.utils import move_to_index
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    n = args.envs
+    boards, hands, sides, mcs, (n_h, n_e, n_c) = cfg5_positions(n)
+    env = VecShogiEnv(n, MAX_MOVES, dev, seed=SEED, env_offset=rank * n, auto_reset=True)
+    env.load_positions(boards, hands, sides, mcs, eval_termination=False)
+    env.step_index = 0
+    SLOTS = 2
+    obs_buf = torch.zeros((SLOTS, n, 46, 9, 9), dtype=torch.float32, device=dev)
+    mask_buf = torch.zeros((SLOTS, n, MASK_PAD_STRIDE), dtype=torch.uint8, device=dev)
+    act = [torch.zeros(n, dtype=torch.int64, device=dev) for _ in range(2)]
+    env.refresh(random_actions=True, next_out=act[0])
+    cycle = [move_to_index(m) for m in CYCLE_MOVES]
+    hist = torch.zeros(5, dtype=torch.int64, device=dev)
+    senn13 = torch.zeros((), dtype=torch.int64, device=dev)
+    it = [0]
+
+    def step():
+        i = it[0]
+        it[0] += 1
+        a = act[i & 1]
+        if i < 13:
+            a[n_h + n_e:] = cycle[i % 4]  # the scripted third
+        out = env.step(a, obs=obs_buf[i % SLOTS], mask=mask_buf[i % SLOTS][:, :13527], random_actions=True,
+                       next_out=act[(i + 1) & 1])
+        return out
+
+    for i in range(args.preroll + args.warmup):
+        out = step()
+        hist += torch.bincount(out["reason"].long(), minlength=5)
+        if i == 12:
+            senn13 += (out["reason"][n_h + n_e:] == 4).sum()
+    barrier()
+    ply0 = float(env.export()[2][:, 1].float().mean())
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = ev0.elapsed_time(ev1)
+    ply1 = float(env.export()[2][:, 1].float().mean())
+    errs = int((env.errors() != 0).sum())
+    stats = torch.cat([hist, senn13.reshape(1), torch.tensor([errs], device=dev)])
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t)
+        dist.all_reduce(stats)
+    if rank == 0:
+        import ctypes as C
+        from shogidrl_b200 import _native as nv
+        offs, total = (C.c_int64 * 3)(), C.c_int64()
+        nv.lib().kz_state_layout(n, MAX_MOVES, offs, C.byref(total))
+        mean_ply = 0.5 * (ply0 + ply1)
+        peak, peak_src = measured_peak_gbs()
+        achieved = algorithmic_bytes_per_step(mean_ply) * n / (ms_total / args.steps * 1e-3) / 1e9
+        h = stats.tolist()
+        emit({"metric": METRIC, "value": world * n * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+              "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+              "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+              "config": {"workload": f"BASELINE config 5: long-game stress, {n} games per GPU x {world}, max_moves {MAX_MOVES}, "
+                                     f"start mix {n_h} hirate / {n_e} drops-heavy endgames (128 fixed SFENs) / {n_c} 4-ply-cycle "
+                                     f"scripts per GPU, auto-reset to hirate, legal mask + obs + step, random-legal play",
+                         "envs_per_gpu": n, "preroll_steps": args.preroll + args.warmup, "mean_ply": mean_ply,
+                         "state_bytes_per_gpu": int(total.value), "history_bytes_per_gpu": int(total.value - offs[2]),
+                         "output_ring_bytes_per_gpu": int(obs_buf.numel() * 4 + mask_buf.numel()),
+                         "finished_games_by_reason": {"Tsumi": h[1], "stalemate": h[2], "Max moves reached": h[3], "Sennichite": h[4]},
+                         "scripted_cycles_ended_by_sennichite_on_ply_13": f"{h[5]} of {n_c * world}",
+                         "env_error_flags": h[6]},
+              "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                           "traffic": None, "kernel": "kz_step_kernel", "kernel_ms": ms_total / args.steps, "peak_source": peak_src},
+              "gpu_launches": args.steps, "clocks": clocks})
+    finish_process_group(world)
     return 0
 
 
@@ -488,24 +729,43 @@ def emit(line):
     out.flush()
 
 
-def run_ppo(args):
-    """--workload ppo: BASELINE config 3 -- PPO self-play with the default CNN policy-value net (bf16 autocast),
-    16,384 envs, rollout T = 128, fused masked sampling, device GAE, then the PPO update.  One step = one full
-    epoch (collect + update); value = samples (env steps) per second end to end; rollout-only rate in config."""
+# algorithmic bytes per rollout sample (configs 3/4) = B_env + the tower's re-read of the observation
+# + logits written and read once (bf16) + the sampler's read of the mask row + action / log-prob / value writes
+def rollout_bytes_per_sample(mean_ply: float) -> float:
+    return algorithmic_bytes_per_step(mean_ply) + OBS_B + 2 * 13527 * 2 + MASK_B + 16
+
+
+def tower_mfu(model_kind: str, samples_per_gpu_epoch: int, ppo_epochs: int, epoch_ms: float):
+    """Dense-contraction throughput of the policy/value tower (the only tensor-core work on the path): forward FLOPs per
+    sample measured by SURVEY section 8(d) (ActorCritic 36.1 MFLOP, ResTower 9x256 SE 1.74 GFLOP); a PPO sample costs one
+    rollout forward + ppo_epochs x (forward + backward = 3 forwards).  Against the measured sustained bf16 rate."""
+    fwd = 1.74e9 if model_kind == "resnet" else 36.1e6
+    flop = samples_per_gpu_epoch * fwd * (1 + 3 * ppo_epochs)
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak = float(json.load(f)["bf16_tflops_sustained"])
+        src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    except Exception:
+        peak, src = 1400.0, "fallback"
+    tf = flop / (epoch_ms * 1e-3) / 1e12
+    return {"fwd_flop_per_sample": fwd, "fwd_equivalents_per_sample": 1 + 3 * ppo_epochs, "achieved_tflops_per_gpu": tf,
+            "peak_tflops": peak, "mfu": tf / peak, "peak_source": src}
+
+
+def measure_ppo(args, dev, world, rank, barrier):
+    """BASELINE config 3 (or 4 with --ppo-model resnet): PPO self-play with the policy-value net under bf16 autocast,
+    `--ppo-envs` games per GPU, rollout T = `--ppo-horizon` (tower forward, fused masked sampling on the engine's legal
+    bitmaps, engine step writing observations / bitmaps / rewards straight into the rollout buffer, device GAE), then the
+    PPO update (ppo_epochs x minibatches, fused masked evaluation, loss, clip + Adam, replayed from a CUDA graph).  One
+    step = one epoch (collect + update).  Returns the `ppo` record (rank 0) or None."""
     import torch
     import torch.distributed as dist
     from types import SimpleNamespace
+    from shogidrl_b200 import rl
     from shogidrl_b200.core import ActorCritic, ActorCriticResTower
     from shogidrl_b200.training.selfplay import SelfPlayTrainer
 
-    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    N, T = args.ppo_envs, args.ppo_horizon
-    mb = args.ppo_minibatch
+    N, T, mb = args.ppo_envs, args.ppo_horizon, args.ppo_minibatch
     cfg = SimpleNamespace(
         env=SimpleNamespace(device=str(dev), seed=SEED, input_channels=46, num_actions_total=13527, max_moves_per_game=MAX_MOVES),
         training=SimpleNamespace(learning_rate=3e-4, gamma=0.99, lambda_gae=0.95, clip_epsilon=0.2, value_loss_coeff=0.5,
@@ -520,58 +780,147 @@ def run_ppo(args):
     else:
         model = ActorCritic(46, 13527)
     tr = SelfPlayTrainer(model, cfg, N, T, dev, use_mixed_precision=True)
+    for _ in range(max(1, args.ppo_warmup)):
+        tr.run_epoch()
+    barrier()
+    sampler = ClockSampler(dev.index or 0)
+    if rank == 0:
+        sampler.start()
+    steps = args.ppo_steps
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    roll_ms = upd_ms = 0.0
+    m = {}
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ev[0].record(); tr.collect(); ev[1].record(); m = tr.update(); ev[2].record()
+        torch.cuda.synchronize(dev)
+        roll_ms += ev[0].elapsed_time(ev[1]); upd_ms += ev[1].elapsed_time(ev[2])
+    barrier()
+    total_ms = 1e3 * (time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
+    mean_ply = float(tr.env.export()[2][:, 1].float().mean())
+
+    # ---- the hand-written kernels of the path, timed live on this run's data (CUDA events, current stream)
+    b = tr.buffer
+    kern = {}
+
+    def timed(fn, reps=20):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    peak, peak_src = measured_peak_gbs()
+    rows = min(mb, N)
+    logits = torch.randn((rows, 13536), device=dev).bfloat16()[:, :13527]
+    legal = float(tr.env.legal_count.float().mean())  # legal actions per position (~50 under a near-uniform policy)
+    bm = b.bitmaps[1][:rows]
+    acts = b.actions[1][:rows].contiguous()
+    sectors = legal * 32.0  # one 32-byte sector per legal logit
+    ms = timed(lambda: rl.sample_masked(logits, bm, seed=1, offset=0))
+    kern["kz_sample_bitmap"] = {"ms": ms, "rows": rows, "survey_bytes_per_row": 13527 * 2 + 13527,
+                                "implementation_bytes_per_row": 1792 + sectors + 12}
+    lg = logits.detach().clone().requires_grad_(True)
+    lp, en = rl.evaluate_masked(lg, bm, acts)
+    ms = timed(lambda: rl.evaluate_masked(lg, bm, acts))
+    kern["kz_eval_bitmap_fwd"] = {"ms": ms, "rows": rows, "survey_bytes_per_row": 13527 * 2 + 13527,
+                                  "implementation_bytes_per_row": 1792 + 2 * sectors + 24}
+    g1, g2 = torch.ones_like(lp), torch.ones_like(en)
+    ms_fb = timed(lambda: torch.autograd.grad((lp, en), lg, (g1, g2), retain_graph=True))
+    kern["kz_eval_bitmap_bwd"] = {"ms": ms_fb, "rows": rows, "survey_bytes_per_row": 13527 * 2 + 13527 + 13527 * 2,
+                                  "implementation_bytes_per_row": 1792 + sectors + 13536 * 2 + 16,
+                                  "note": "includes the dense dlogits row (27 KB) the two gradient GEMMs read"}
+    for k in kern.values():
+        t = k["ms"] * 1e-3
+        k["achieved_gbs"] = k["survey_bytes_per_row"] * k["rows"] / t / 1e9
+        k["achieved_implementation_gbs"] = k["implementation_bytes_per_row"] * k["rows"] / t / 1e9
+        k["frac_implementation_bytes"] = k["achieved_implementation_gbs"] / peak
+    del lg, lp, en, logits
+
+    if world > 1:
+        t = torch.tensor([total_ms, roll_ms, upd_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, roll_ms, upd_ms = [float(x) for x in t]
+    rec = None
+    if rank == 0:
+        samples = world * N * T * steps
+        n_upd = -(-N * T // mb) * args.ppo_epochs
+        cnn = args.ppo_model == "cnn"
+        rb = rollout_bytes_per_sample(mean_ply)
+        rec = {"metric": "PPO self-play samples/sec", "value": samples / (total_ms * 1e-3), "unit": "samples/s",
+               "n_gpus": world, "steps": steps, "warmup": max(1, args.ppo_warmup), "ms_per_step": total_ms / steps,
+               "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
+               "config": {"workload": f"BASELINE config {3 if cnn else 4}: PPO self-play, {args.ppo_model} policy-value net "
+                                      f"(bf16 autocast), {N} envs/GPU, T={T}, fused masked sampling on legal bitmaps + device "
+                                      f"GAE, ppo_epochs={args.ppo_epochs}, minibatch={mb} ({n_upd} updates per epoch)",
+                          "envs_per_gpu": N, "horizon": T, "minibatch": mb, "ppo_epochs": args.ppo_epochs,
+                          "parallelism": f"env-shard x{world}, gradient all-reduce over NCCL in the update" if world > 1 else "1 GPU",
+                          "rollout_storage_gb": (b.obs.numel() * 4 + b.bitmaps.numel() * 4) / 1e9},
+               "rollout_samples_per_s": samples / (roll_ms * 1e-3), "update_samples_per_s": samples / (upd_ms * 1e-3),
+               "rollout_ms": roll_ms / steps, "update_ms": upd_ms / steps,
+               "rollout_step_ms": roll_ms / steps / T, "update_minibatch_ms": upd_ms / steps / n_upd,
+               "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
+                            "rollout": {"bytes_per_sample": rb, "achieved": rb * N * T / (roll_ms / steps * 1e-3) / 1e9,
+                                        "frac": rb * N * T / (roll_ms / steps * 1e-3) / 1e9 / peak,
+                                        "note": "SURVEY section 8(d) bytes per rollout sample over the whole rollout step "
+                                                "(tower GEMM included, which is tensor-bound, not HBM-bound)"},
+                            "kernels": kern},
+               "tower": tower_mfu(args.ppo_model, N * T, args.ppo_epochs, total_ms / steps),
+               "last_metrics": {k: float(v) for k, v in m.items()},
+               "clocks": clocks,
+               # own kernels per epoch: rollout steps (kz_step, kz_sample_bitmap, + kz_obs_conv_fwd for the CNN), kz_gae, and per
+               # minibatch update kz_eval_bitmap_fwd/bwd, kz_ppo_loss, 3 x kz_adam_clip (+ kz_obs_conv_fwd and 2 wgrad kernels)
+               "gpu_launches": steps * (T * (3 if cnn else 2) + 1 + n_upd * (9 if cnn else 6))}
+    if world > 1:
+        # the captured update graph holds NCCL work: release it before the process group goes away
+        import gc
+        barrier()
+        tr.agent._drop_graph()
+        gc.collect()
+        torch.cuda.synchronize(dev)
+    del tr
+    return rec
+
+
+def run_ppo(args):
+    """--workload ppo: the PPO record as its own JSON line (the default env workload carries it as line["ppo"])."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(1, args.warmup if args.warmup < 3 else 1)):
-        tr.run_epoch()
-    barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    roll_ms = upd_ms = 0.0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ev[0].record(); tr.collect(); ev[1].record(); m = tr.update(); ev[2].record()
-        torch.cuda.synchronize(dev)
-        roll_ms += ev[0].elapsed_time(ev[1]); upd_ms += ev[1].elapsed_time(ev[2])
-    barrier()
-    total_ms = 1e3 * (time.perf_counter() - t0)
-    if world > 1:
-        t = torch.tensor([total_ms, roll_ms, upd_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, roll_ms, upd_ms = [float(x) for x in t]
+    args.ppo_steps = args.steps if args.steps <= 16 else 2
+    rec = measure_ppo(args, dev, world, rank, barrier)
     if rank == 0:
-        samples = world * N * T * args.steps
-        line = {"metric": "PPO self-play samples/sec", "value": samples / (total_ms * 1e-3), "unit": "samples/s",
-                "n_gpus": world, "steps": args.steps, "warmup": 1, "ms_per_step": total_ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": f"BASELINE config {3 if args.ppo_model == 'cnn' else 4}: PPO self-play, {args.ppo_model} policy-value net (bf16 autocast), {N} envs/GPU, "
-                                       f"T={T}, fused masked sampling + device GAE, ppo_epochs={args.ppo_epochs}, minibatch={mb}",
-                           "rollout_samples_per_s": samples / (roll_ms * 1e-3), "update_samples_per_s": samples / (upd_ms * 1e-3),
-                           "rollout_ms": roll_ms / args.steps, "update_ms": upd_ms / args.steps,
-                           "last_metrics": {k: float(v) for k, v in m.items()}},
-                # own kernels per epoch: rollout steps (kz_step, kz_sample_masked, + kz_obs_conv_fwd for the CNN), kz_gae,
-                # and per minibatch update kz_eval_masked_fwd/bwd (+ kz_obs_conv_fwd and the two wgrad kernels)
-                "gpu_launches": args.steps * (T * (3 if args.ppo_model == "cnn" else 2) + 1
-                                              + -(-N * T // mb) * args.ppo_epochs * (5 if args.ppo_model == "cnn" else 2))}
-        emit(line)
+        rec["vs_baseline"] = None
+        emit(rec)
+    finish_process_group(world)
+    return 0
+
+
+def finish_process_group(world):
+    """Never let a stuck communicator teardown outlive the measurement."""
     if world > 1:
-        # the captured update graph holds NCCL work: release it before the process group goes away, and never let
-        # a stuck communicator teardown outlive the measurement
-        import gc
         import threading
-        barrier()
-        tr.agent._graph = None
-        gc.collect()
-        torch.cuda.synchronize(dev)
+        import torch.distributed as dist
         killer = threading.Timer(30.0, lambda: os._exit(0))
         killer.daemon = True
         killer.start()
         dist.destroy_process_group()
         killer.cancel()
-    return 0
 
 
 def main():
@@ -583,15 +932,21 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="games per GPU (BASELINE config 2: 65,536)")
     ap.add_argument("--preroll", type=int, default=PREROLL)
     ap.add_argument("--step-streams", type=int, default=None,
-                    help="ranges of games a step is launched as, on as many streams (default: VecShogiEnv's choice, 2 for >= 32,768 games)")
+                    help="ranges of games a step is launched as, on as many streams (kz_step_range; default 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="env", choices=["env", "ppo"], help="env: BASELINE config 2 (default, the headline); ppo: config 3")
+    ap.add_argument("--workload", default="env", choices=["env", "ppo", "cfg5"],
+                    help="env: BASELINE config 2 (default, the headline; carries the config-3 PPO record); ppo: config 3 (or 4 with "
+                         "--ppo-model resnet --ppo-envs 32768) as its own line; cfg5: the long-game stress (--envs 262144)")
     ap.add_argument("--ppo-envs", type=int, default=16384)
     ap.add_argument("--ppo-horizon", type=int, default=128)
     ap.add_argument("--ppo-epochs", type=int, default=10)
     ap.add_argument("--ppo-minibatch", type=int, default=16384)
     ap.add_argument("--ppo-model", default="cnn", choices=["cnn", "resnet"])
     ap.add_argument("--ref-ppo-steps", type=int, default=512, help="timesteps per epoch of the CPU PPO reference arm")
+    ap.add_argument("--ref-same-minibatch", action="store_true", help="--impl reference --workload ppo: minibatch = min(--ppo-minibatch, steps) instead of the reference's 64")
+    ap.add_argument("--no-ppo", action="store_true", help="skip the PPO (config 3) record of the default workload")
+    ap.add_argument("--ppo-steps", type=int, default=2, help="timed PPO epochs of the `ppo` record")
+    ap.add_argument("--ppo-warmup", type=int, default=1, help="untimed PPO epochs (the first also captures the update graph)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -605,6 +960,10 @@ def main():
     isolate_stdout()
     if args.workload == "ppo":
         return run_ppo(args)
+    if args.workload == "cfg5":
+        if args.envs == ENVS_PER_GPU:
+            args.envs = 262144
+        return run_cfg5(args)
     return run_product(args)
 
 

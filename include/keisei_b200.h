@@ -54,6 +54,8 @@ extern "C" {
 
 int kz_abi_version(void);
 const char* kz_last_cuda_error(void);
+/* "src_sha=<sha256/16 of csrc/*.cu, *.cuh and this header at build time> built=<date time> arch=sm_100a" */
+const char* kz_build_info(void);
 
 /* Move/ray lookup tables -> device memory of the current device.  Idempotent. */
 int kz_init_tables(void* stream);
@@ -123,8 +125,9 @@ int kz_step(void* state, int n, int hist_cap, const void* actions, int actions_i
  * still indexed by the game's position in the whole batch (row g of obs / mask / bitmap, element g of actions, reward,
  * ...), and the per-game random stream is keyed by env_offset + g as before, so stepping a batch as several ranges gives
  * exactly the results of one kz_step.  Ranges of one batch may run CONCURRENTLY on different streams when each names its
- * own counter_slot (0..63, the dynamic work counter of the launch): the CTAs of the second range fill the SMs that the
- * first range's tail leaves idle (a persistent grid drains unevenly), -5 % per 65,536-game step on B200.
+ * own counter_slot (0..63, the dynamic work counter of the launch): a caller that consumes each range's results
+ * separately can let the ranges run ahead of each other across steps, so that one range's CTAs fill the SMs another
+ * range's draining grid leaves idle.
  * mask != NULL: byte-mask form (kz_step); bitmap != NULL: rollout form (kz_step_rollout); not both. */
 int kz_step_range(void* state, int n, int hist_cap, int first, int count, int counter_slot, const void* actions,
                   int actions_i64, float* obs, int64_t obs_stride, uint8_t* mask, int64_t mask_stride, uint32_t* bitmap,

@@ -414,6 +414,43 @@ int orc_legal_mask(orc_game *g, uint8_t *mask) { /* utils.py:310-336 */
 
 int orc_in_check(const orc_game *g, int color) { return king_in_check(g->board, color); }
 
+/* generate_piece_potential_moves (shogi_rules_logic.py:82-208) of the piece on sq: out81[t] = 1 for every target */
+int orc_piece_targets(const orc_game *g, int sq, uint8_t *out81) {
+  memset(out81, 0, NSQ);
+  if (sq < 0 || sq >= NSQ || g->board[sq] == 0) return 0;
+  int t[64];
+  int n = potential_moves(g->board, g->board[sq], sq / 9, sq % 9, t);
+  for (int i = 0; i < n; i++) out81[t[i]] = 1;
+  return n;
+}
+
+/* ShogiGame.is_uchi_fu_zume (shogi_game.py:237-241 -> check_for_uchi_fu_zume, shogi_rules_logic.py:275-359) */
+int orc_uchi_fu_zume(orc_game *g, int sq, int color) { return uchi_fu_zume(g, sq, color); }
+
+/* ShogiGame.can_drop_piece (shogi_game.py:243-260 -> can_drop_specific_piece, shogi_rules_logic.py:424-483), after the
+ * facade's own guards: piece in hand, square on the board */
+int orc_can_drop(orc_game *g, int type, int sq, int color) {
+  if (type < 0 || type > 6 || sq < 0 || sq >= NSQ) return 0;
+  if (g->hands[color][type] <= 0) return 0;
+  return can_drop(g, type, sq, color, 0);
+}
+
+/* ShogiGame.get_king_legal_moves (shogi_game.py:208-235): legal moves of `color` whose mover is the king */
+int orc_king_legal_moves(orc_game *g, int color) {
+  if (find_king(g->board, color) < 0) return 0;
+  int saved = g->side;
+  g->side = color;
+  uint16_t tmp[1024];
+  int n = gen_legal(g, 0, tmp), k = 0;
+  for (int i = 0; i < n; i++) {
+    if (tmp[i] >= 12960) continue;
+    int from = (tmp[i] >> 1) / 80;
+    if (ptype(g->board[from]) == T_KING) k++;
+  }
+  g->side = saved;
+  return k;
+}
+
 /* generate_neural_network_observation: shogi_game_io.py:434-539 */
 void orc_observation(const orc_game *g, float *obs) {
   memset(obs, 0, sizeof(float) * 46 * NSQ);

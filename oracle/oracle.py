@@ -55,6 +55,14 @@ def lib() -> C.CDLL:
         L.orc_legal_mask.restype = i32
         L.orc_in_check.argtypes = [vp, i32]
         L.orc_in_check.restype = i32
+        L.orc_piece_targets.argtypes = [vp, i32, vp]
+        L.orc_piece_targets.restype = i32
+        L.orc_uchi_fu_zume.argtypes = [vp, i32, i32]
+        L.orc_uchi_fu_zume.restype = i32
+        L.orc_can_drop.argtypes = [vp, i32, i32, i32]
+        L.orc_can_drop.restype = i32
+        L.orc_king_legal_moves.argtypes = [vp, i32]
+        L.orc_king_legal_moves.restype = i32
         L.orc_observation.argtypes = [vp, vp]
         L.orc_make_move.argtypes = [vp, i32, vp]
         L.orc_make_move.restype = i32
@@ -173,6 +181,21 @@ class OracleGame:
 
     def in_check(self, color: int) -> bool:
         return bool(self._L.orc_in_check(self._g, color))
+
+    def piece_targets(self, sq: int) -> np.ndarray:
+        """generate_piece_potential_moves (shogi_rules_logic.py:82-208) of the piece on ``sq`` as uint8[81]."""
+        out = np.zeros(81, np.uint8)
+        self._L.orc_piece_targets(self._g, int(sq), _p(out))
+        return out
+
+    def is_uchi_fu_zume(self, sq: int, color: int) -> bool:
+        return bool(self._L.orc_uchi_fu_zume(self._g, int(sq), int(color)))
+
+    def can_drop(self, piece_type: int, sq: int, color: int) -> bool:
+        return bool(self._L.orc_can_drop(self._g, int(piece_type), int(sq), int(color)))
+
+    def king_legal_moves(self, color: int) -> int:
+        return int(self._L.orc_king_legal_moves(self._g, int(color)))
 
     def observation(self) -> np.ndarray:
         o = np.zeros((46, 9, 9), np.float32)

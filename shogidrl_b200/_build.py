@@ -31,10 +31,24 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def source_sha() -> str:
+    """sha256 (first 16 hex digits) over the CUDA sources and the C header, in a fixed order: baked into the library at
+    build time (kz_build_info) so that a benchmark line can show which sources the loaded .so was built from."""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))
+    files.append(os.path.join(os.path.dirname(HERE), "include", "keisei_b200.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode() + b"\0")
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def build_native(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    cmd = [_nvcc()] + NVCC_FLAGS + [f'-DKZ_SRC_SHA="{source_sha()}"'] + (["-Xptxas", "-v"] if verbose else []) + \
           [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
     env = dict(os.environ)
     env.pop("CC", None)

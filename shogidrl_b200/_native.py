@@ -20,7 +20,7 @@ BITMAP_WORDS = 448
 REASONS = {0: None, 1: "Tsumi", 2: "stalemate", 3: "Max moves reached", 4: "Sennichite"}
 
 EXPORTS = [
-    "kz_abi_version", "kz_last_cuda_error", "kz_init_tables", "kz_state_layout", "kz_reset", "kz_load_positions",
+    "kz_abi_version", "kz_last_cuda_error", "kz_build_info", "kz_init_tables", "kz_state_layout", "kz_reset", "kz_load_positions",
     "kz_export_positions", "kz_piece_targets", "kz_refresh", "kz_step", "kz_legal_mask", "kz_observe", "kz_errors", "kz_sample_masked",
     "kz_gae", "kz_gae_exact", "kz_eval_masked_fwd", "kz_eval_masked_bwd", "kz_obs_conv_fwd", "kz_obs_conv_wgrad_ctas",
     "kz_obs_conv_wgrad", "kz_ppo_loss", "kz_eval_masked_bwd_bias", "kz_adam_clip_workspace", "kz_adam_clip_step",
@@ -51,6 +51,7 @@ def lib() -> C.CDLL:
     vp, i32, i64, u64, u32, f32, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_float, C.c_double
     L.kz_abi_version.restype = i32
     L.kz_last_cuda_error.restype = C.c_char_p
+    L.kz_build_info.restype = C.c_char_p
     L.kz_init_tables.argtypes = [vp]
     L.kz_state_layout.argtypes = [i32, i32, C.POINTER(i64), C.POINTER(i64)]
     L.kz_reset.argtypes = [vp, i32, i32, vp, i32, vp]
@@ -86,13 +87,28 @@ def lib() -> C.CDLL:
     L.kz_obs_conv_wgrad.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, i32, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("kz_last_cuda_error",):
+        if name not in ("kz_last_cuda_error", "kz_build_info"):
             fn.restype = i64 if name == "kz_adam_clip_workspace" else i32
     if L.kz_abi_version() != ABI_VERSION:
         raise NativeError(f"{LIB_PATH} has ABI version {L.kz_abi_version()}, this package binds version {ABI_VERSION}: "
                           "rebuild it (python -c 'import __graft_entry__ as g; g.build()')")
     _lib = L
     return L
+
+
+def build_info() -> dict:
+    """{"src_sha": hash of the sources the loaded library was built from, "built": ..., "src_sha_now": hash of the
+    sources in the tree, "match": whether they agree, "lib": path}."""
+    import re
+    from . import _build
+    m = re.match(r"src_sha=(\S+) built=(.*) arch=(\S+)", lib().kz_build_info().decode())
+    info = {"src_sha": m.group(1), "built": m.group(2), "arch": m.group(3)} if m else {"src_sha": None}
+    try:
+        now = _build.source_sha()
+    except OSError:
+        now = None
+    info.update(src_sha_now=now, match=(now == info.get("src_sha")), lib=LIB_PATH)
+    return info
 
 
 def check(rc: int, what: str) -> None:
@@ -109,6 +125,13 @@ def require(cond: bool, what: str) -> None:
 
 
 def stream_ptr(device: torch.device) -> int:
+    """torch's current stream on ``device`` -- the last argument of every launch.  The library launches on the CALLING
+    THREAD's current CUDA device (one process per GPU with torch.cuda.set_device(local_rank) is the supported layout), so
+    tensors on another device are refused here instead of failing inside the launch with "invalid resource handle"."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx != torch.cuda.current_device():
+        raise NativeError(f"tensors live on cuda:{idx} but the current CUDA device is cuda:{torch.cuda.current_device()}: call "
+                          f"torch.cuda.set_device({idx}) (or wrap the call in `with torch.cuda.device({idx}):`) first")
     return torch.cuda.current_stream(device).cuda_stream
 
 

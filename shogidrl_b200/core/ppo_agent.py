@@ -235,8 +235,9 @@ class PPOAgent:
         self.optimizer.zero_grad(set_to_none=True)
         loss.backward()  # under DistributedDataParallel the gradient all-reduce (NCCL) fires here
         if grad_world > 1:
-            from ..training import distributed as kd
-            kd.all_reduce_grads(self.model.parameters())
+            # sum over ranks (the loss was scaled by 1 / world): the policy head's weight gradient has been on its way since
+            # its GEMM finished inside backward; the small gradients go as one flattened buffer
+            self._reducer.finish(self.model.parameters())
         if self._fused_optimizer:
             # global-norm clip + Adam on the optimizer's own state tensors in three launches (csrc/kz_opt.cu)
             gn = rl.adam_clip_step(self.optimizer, self.gradient_clip_max_norm, self._gn2)
@@ -319,8 +320,11 @@ class PPOAgent:
         if world == 1:
             return
         if getattr(self.model, "fused_minibatch", False):
+            from .. import nn_ops
             kd.broadcast_module(self.model)
             self._grad_world = world
+            self._reducer = kd.GradReducer()
+            nn_ops.grad_reducer = self._reducer
         else:
             self._ddp = kd.wrap_ddp(self.model, self.device)
 

@@ -1528,9 +1528,13 @@ int kz_cuda_fail(cudaError_t e) { return cuda_fail(e); }  // shared with kz_rl.c
 namespace {
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return cuda_fail(_e); } while (0)
 
-int g_sm_count = 0;
-
-bool g_host_ready = false;
+// per device (kz_init_tables runs once per device: the tables are __device__ symbols of the current device)
+constexpr int kMaxDevices = 64;
+int g_sm_counts[kMaxDevices] = {0};
+bool g_ready[kMaxDevices] = {false};
+inline int cur_device() { int d = 0; return cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < kMaxDevices ? d : -1; }
+inline bool host_ready() { const int d = cur_device(); return d >= 0 && g_ready[d]; }
+inline int sm_count() { const int d = cur_device(); return d >= 0 ? g_sm_counts[d] : 0; }
 
 struct Layout { int64_t off_boards, off_meta, off_hist, off_sched, total; int rep_slots; };
 Layout layout(int n, int hist_cap) {
@@ -1550,7 +1554,7 @@ int launch_step(void* state, int n, int hist_cap, StepParams P, cudaStream_t st,
   if (!state || n <= 0 || hist_cap < 0 || hist_cap > 65535) return KZ_E_ARG;
   if (count < 0) count = n - first;
   if (first < 0 || count <= 0 || first + count > n || slot < 0 || slot >= 64) return KZ_E_ARG;
-  if (!g_host_ready) return KZ_E_NOT_INIT;
+  if (!host_ready()) return KZ_E_NOT_INIT;
   if (((uintptr_t)state & 255) != 0) return KZ_E_ARG;
   const Layout L = layout(n, hist_cap);
   uint8_t* base = reinterpret_cast<uint8_t*>(state);
@@ -1575,7 +1579,7 @@ int launch_step(void* state, int n, int hist_cap, StepParams P, cudaStream_t st,
   }
   const int ctas_needed = (count + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   // mode 2 without observation rows is the split pipeline's generator (leaves room for kz_expand_kernel beside it)
-  int grid = g_sm_count * ((P.mode == 2 && !P.obs) ? KZ_COMPACT_CTAS_PER_SM : CTAS_PER_SM);
+  int grid = sm_count() * ((P.mode == 2 && !P.obs) ? KZ_COMPACT_CTAS_PER_SM : CTAS_PER_SM);
   if (grid > ctas_needed) grid = ctas_needed;
   const size_t dyn = sizeof(WarpScratch) * WARPS_PER_CTA;
   P.tile_counter = nullptr;
@@ -1599,6 +1603,10 @@ int launch_step(void* state, int n, int hist_cap, StepParams P, cudaStream_t st,
 extern "C" {
 
 int kz_abi_version(void) { return KZ_ABI_VERSION; }
+#ifndef KZ_SRC_SHA
+#define KZ_SRC_SHA "unknown"
+#endif
+const char* kz_build_info(void) { return "src_sha=" KZ_SRC_SHA " built=" __DATE__ " " __TIME__ " arch=sm_100a"; }
 const char* kz_last_cuda_error(void) { return t_cuda_err; }
 
 int kz_state_layout(int n, int hist_cap, int64_t* offsets3, int64_t* total_bytes) {
@@ -1678,14 +1686,15 @@ int kz_init_tables(void* stream) {
   CK(cudaMemcpyToSymbolAsync(c_init_board, init, sizeof init, 0, cudaMemcpyHostToDevice, st));
   int dev = 0;
   CK(cudaGetDevice(&dev));
-  CK(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+  if (dev < 0 || dev >= kMaxDevices) return KZ_E_ARG;
+  CK(cudaDeviceGetAttribute(&g_sm_counts[dev], cudaDevAttrMultiProcessorCount, dev));
   {  // per-warp scratch lives in dynamic shared memory (more than 48 KB with tables for CTAs above 8 warps)
     const int dyn = (int)(sizeof(WarpScratch) * WARPS_PER_CTA);
     CK(cudaFuncSetAttribute(kz_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
     CK(cudaFuncSetAttribute(kz_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
     CK(cudaFuncSetAttribute(kz_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
   }
-  g_host_ready = true;
+  g_ready[dev] = true;
   // legal bitmap of the start position, computed once by the engine itself on a scratch game
   {
     const Layout L = layout(1, 0);
@@ -1714,7 +1723,7 @@ int kz_init_tables(void* stream) {
 
 int kz_reset(void* state, int n, int hist_cap, const uint8_t* env_mask, int max_moves, void* stream) {
   if (!state || n <= 0 || max_moves < 0 || max_moves > 65535) return KZ_E_ARG;
-  if (!g_host_ready) return KZ_E_NOT_INIT;
+  if (!host_ready()) return KZ_E_NOT_INIT;
   const Layout L = layout(n, hist_cap);
   uint8_t* base = reinterpret_cast<uint8_t*>(state);
   kz_reset_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
@@ -1748,7 +1757,7 @@ int kz_export_positions(const void* state, int n, int hist_cap, int8_t* boards, 
 
 int kz_piece_targets(const void* state, int n, int hist_cap, const int32_t* squares, uint32_t* targets3, void* stream) {
   if (!state || n <= 0 || !squares || !targets3) return KZ_E_ARG;
-  if (!g_host_ready) return KZ_E_NOT_INIT;
+  if (!host_ready()) return KZ_E_NOT_INIT;
   const Layout L = layout(n, hist_cap);
   const uint8_t* base = reinterpret_cast<const uint8_t*>(state);
   kz_targets_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(base + L.off_boards, n, squares, targets3);
@@ -1827,7 +1836,7 @@ int kz_step_compact(void* state, int n, int hist_cap, const void* actions, int a
 int kz_expand(const void* state, int n, int hist_cap, const uint32_t* bitmap, float* obs, int64_t obs_stride,
               uint8_t* mask, int64_t mask_stride, void* stream) {
   if (!state || n <= 0 || hist_cap < 0 || hist_cap > 65535 || !bitmap || (!obs && !mask)) return KZ_E_ARG;
-  if (!g_host_ready) return KZ_E_NOT_INIT;
+  if (!host_ready()) return KZ_E_NOT_INIT;
   if (obs && ((((uintptr_t)obs) & 15) || (obs_stride & 1) || obs_stride < KZ_OBS_FLOATS)) return KZ_E_ARG;
   int mask_vec = 0;
   if (mask) {
@@ -1837,7 +1846,7 @@ int kz_expand(const void* state, int n, int hist_cap, const uint32_t* bitmap, fl
   }
   const Layout L = layout(n, hist_cap);
   const uint8_t* base = reinterpret_cast<const uint8_t*>(state);
-  int grid = g_sm_count * KZ_EXPAND_CTAS_PER_SM;
+  int grid = sm_count() * KZ_EXPAND_CTAS_PER_SM;
   if (grid > (n + 7) / 8) grid = (n + 7) / 8;
   kz_expand_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(base + L.off_boards, base + L.off_meta, bitmap, n,
                                                                             obs, obs_stride, mask, mask_stride, mask_vec);

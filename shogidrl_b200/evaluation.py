@@ -37,19 +37,26 @@ def evaluate_vs_opponent(agent, num_games: int, *, opponent=None, num_envs: int 
                          device="cuda", seed: int = 0, deterministic: bool = True,
                          max_steps: Optional[int] = None) -> EvaluationResult:
     """Play ``num_games`` games of ``agent`` against ``opponent`` (None = uniform-random legal moves).  The agent
-    plays Black in even-numbered envs and White in odd-numbered ones.  Every tensor stays on the device; the host
-    reads four counters per step."""
+    plays Black in even-numbered envs and White in odd-numbered ones.  Every env has a fixed QUOTA of games
+    (``num_games`` spread evenly over the envs): the first ``quota`` games an env finishes are counted and later ones
+    are ignored, so the sample is ``num_games`` independent games exactly as the reference's sequential loop plays them
+    -- counting "the first num_games completions of the batch" would over-sample short (decisive) games, because a
+    fast env restarts and finishes again while the long draws are still running.  Every tensor stays on the device;
+    the host reads four counters per step."""
     n = min(num_envs, max(2, num_games))
     env = VecShogiEnv(n, max_moves_per_game=max_moves_per_game, device=device, seed=seed, auto_reset=True)
     dev = env.device
     agent_is_black = (torch.arange(n, device=dev) % 2) == 0
+    quota = torch.full((n,), num_games // n, dtype=torch.int64, device=dev)
+    quota[: num_games % n] += 1
+    completed = torch.zeros(n, dtype=torch.int64, device=dev)
     env.refresh(random_actions=True)
     # side to move per env: read from plane 42 of the observation (1.0 = Black to move)
     done_games = agent_w = opp_w = draws = 0
     length_sum = 0
     outcomes: List[str] = []
     steps = 0
-    limit = max_steps if max_steps is not None else 4 * max_moves_per_game * (1 + num_games // n)
+    limit = max_steps if max_steps is not None else (max_moves_per_game + 1) * (1 + num_games // n) + 8
     while done_games < num_games and steps < limit:
         black_to_move = env.obs[:, 42, 0, 0] > 0.5
         agent_turn = black_to_move == agent_is_black
@@ -61,7 +68,8 @@ def evaluate_vs_opponent(agent, num_games: int, *, opponent=None, num_envs: int 
         actions = torch.where(agent_turn, a_agent, a_opp).contiguous()
         out = env.step(actions, random_actions=opponent is None)
         steps += 1
-        d = out["done"] != 0
+        d = (out["done"] != 0) & (completed < quota)  # finished games that still count towards their env's quota
+        completed += d
         if bool(d.any()):
             w = out["winner"]
             agent_won = d & (((w == 0) & agent_is_black) | ((w == 1) & ~agent_is_black))

@@ -20,6 +20,9 @@ from . import _native as nv
 _LD = (nv.NUM_ACTIONS + 15) // 16 * 16
 
 
+grad_reducer = None  # set by PPOAgent.enable_ddp (training.distributed.GradReducer): early all-reduce of the head's weight gradient
+
+
 def _is_bitmap(mask: torch.Tensor) -> bool:
     return mask.dtype == torch.int32 and mask.shape[-1] == nv.BITMAP_WORDS
 
@@ -125,8 +128,12 @@ class _PolicyHeadEval(torch.autograd.Function):
             nv.check(nv.lib().kz_eval_masked_bwd_bias(*common, dbq.data_ptr(), nv.stream_ptr(dev)), "kz_eval_masked_bwd_bias")
         else:
             nv.check(nv.lib().kz_eval_masked_bwd(*common, nv.stream_ptr(dev)), "kz_eval_masked_bwd")
-        dh = torch.mm(dlogits, wp).to(ctx.hdtype) if ctx.needs_input_grad[0] else None
+        # the weight gradient first: under data parallelism its all-reduce (the bulk of the model's gradient bytes) starts
+        # here and overlaps the input-gradient GEMM and everything backward still has to do (distributed.GradReducer)
         dw = torch.mm(dlogits.t(), hb)[: nv.NUM_ACTIONS].to(ctx.wdtype) if ctx.needs_input_grad[1] else None
+        if dw is not None and grad_reducer is not None:
+            dw = grad_reducer.early(dw)
+        dh = torch.mm(dlogits, wp).to(ctx.hdtype) if ctx.needs_input_grad[0] else None
         db = (dbq[: nv.NUM_ACTIONS].to(torch.float64) * 2.0 ** -44).to(ctx.wdtype) if want_db else None
         return dh, dw, db, None, None, None
 

@@ -66,6 +66,48 @@ def broadcast_module(module: torch.nn.Module, src: int = 0) -> None:
                 dist.broadcast(t, src)
 
 
+class GradReducer:
+    """Gradient averaging of the fused-minibatch models, overlapped with the rest of backward.
+
+    The default CNN's gradient is one 70 MB tensor (policy_head.weight) plus five small ones.  The big one is the first
+    gradient backward produces (the policy head is the last layer), so its all-reduce is started from inside the
+    policy head's backward node (``nn_ops.policy_head_evaluate`` calls ``early(tensor)``) as an asynchronous NCCL
+    operation and runs over NVLink while the remaining backward kernels (input-gradient GEMM, value head, input-layer
+    weight gradient) execute; ``finish`` then reduces the small gradients as ONE flattened buffer and waits for the big
+    one before the optimizer reads it.  Everything is issued on / joined into the current stream, so a CUDA-graph
+    capture of the update records the collectives and their cross-stream edges like kernels.  With ``gloo`` (CPU tests)
+    the same calls run synchronously."""
+
+    def __init__(self):
+        self._pending = []   # (work handle, tensor) of reductions started early
+        self._early_ids = set()
+
+    def early(self, grad: torch.Tensor) -> torch.Tensor:
+        """Start summing ``grad`` (a freshly computed, contiguous gradient tensor) over the ranks; returns it."""
+        if world()[1] > 1:
+            work = dist.all_reduce(grad, op=dist.ReduceOp.SUM, async_op=True)
+            self._pending.append(work)
+            self._early_ids.add(grad.data_ptr())
+        return grad
+
+    def finish(self, params) -> None:
+        """Reduce every gradient that ``early`` did not take (flattened into one buffer) and wait for the early ones."""
+        if world()[1] <= 1:
+            return
+        rest = [p.grad for p in params if p.grad is not None and p.grad.data_ptr() not in self._early_ids]
+        if rest:
+            flat = torch.cat([g.reshape(-1) for g in rest])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            off = 0
+            for g in rest:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+        for work in self._pending:
+            work.wait()  # the current stream waits for the NCCL stream
+        self._pending.clear()
+        self._early_ids.clear()
+
+
 def all_reduce_grads(params) -> None:
     """Sum the gradients over ranks, one all-reduce per parameter (NCCL over NVLink on GPUs).  Issued on the
     current stream, so a CUDA-graph capture of the update records them like kernels."""

@@ -49,11 +49,13 @@ class VecShogiEnv:
         self.ep_len = torch.zeros(self.n, dtype=torch.int32, device=d)
         self.legal_count = torch.zeros(self.n, dtype=torch.int32, device=d)
         self.step_index = 0
-        # A step of a large batch is launched as `step_streams` ranges of games on as many streams (kz_step_range): a
-        # persistent grid drains unevenly, and the next range's CTAs fill the SMs the previous range's tail leaves idle
-        # (measured -5 % per 65,536-game step).  Results are those of one launch, bit for bit.
+        # A step can be launched as `step_streams` ranges of games on as many streams (kz_step_range; results identical to
+        # one launch).  Off by default: joined back into the caller's stream after every step, the ranges only share the
+        # SMs within one step and the step gets no shorter (measured on B200, 65,536 games: 0.344 ms as one launch, 0.356
+        # as two ranges, 0.364 as four).  What does pay is letting ranges run AHEAD of each other across steps, which
+        # needs a caller that consumes each range's results separately: HostPipelinedEnv.
         if step_streams is None:
-            step_streams = 2 if self.n >= 32768 else 1
+            step_streams = 1
         self.step_streams = max(1, int(step_streams))
         if self.n % (8 * self.step_streams) != 0:
             self.step_streams = 1

@@ -58,6 +58,16 @@ def _worker(rank, world, port, out):
             gathered = [torch.zeros_like(prm) for _ in range(world)]
             dist.all_gather(gathered, prm.detach().clone())
             assert torch.equal(gathered[0], gathered[1])
+        # GradReducer: one gradient reduced early (asynchronously, from inside backward on GPUs), the rest flattened
+        red = kd.GradReducer()
+        ps = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2, 2))]
+        for i, prm in enumerate(ps):
+            prm.grad = torch.full_like(prm, float(10 * rank + i))
+        ps[0].grad = red.early(ps[0].grad)
+        red.finish(ps)
+        for i, prm in enumerate(ps):
+            assert torch.equal(prm.grad, torch.full_like(prm, float(10 * sum(range(world)) + world * i))), (i, prm.grad)
+        assert not red._pending and not red._early_ids
         # a model without the fused path is wrapped in DistributedDataParallel: same property through the wrapper
         from shogidrl_b200.core.base_actor_critic import ActorCriticResTower
         torch.manual_seed(rank)  # different initial weights per rank: the wrapper broadcasts rank 0's

@@ -306,11 +306,14 @@ def test_batched_evaluation_games():
     torch.manual_seed(3)
     agent = PPOAgent(ActorCritic(46, 13527), cfg, torch.device("cuda"), use_mixed_precision=True)
     res = evaluate_vs_opponent(agent, 64, num_envs=64, max_moves_per_game=60, seed=9, deterministic=False)
-    assert res.games >= 64 and res.agent_wins + res.opponent_wins + res.draws == res.games
+    assert res.games == 64 and res.agent_wins + res.opponent_wins + res.draws == res.games
+    # fixed quota per env: exactly num_games results, one per env here (no over-sampling of short games)
+    res3 = evaluate_vs_opponent(agent, 100, num_envs=48, max_moves_per_game=40, seed=4, deterministic=False)
+    assert res3.games == 100 and len(res3.outcomes) == 100
     assert 0 < res.mean_length <= 60 and 0.0 <= res.win_rate <= 1.0
     # agent vs agent also runs
     res2 = evaluate_vs_opponent(agent, 16, opponent=agent, num_envs=16, max_moves_per_game=30, deterministic=False)
-    assert res2.games >= 16
+    assert res2.games == 16
     assert len(res.outcomes) == res.games and res.outcomes.count("agent_win") == res.agent_wins
     assert res.outcomes.count("opponent_win") == res.opponent_wins and res.outcomes.count("draw") == res.draws
 
@@ -431,6 +434,66 @@ def test_graphed_ppo_update_matches_eager():
     for x, y in zip(pa, pb):
         assert torch.allclose(x, y, rtol=1e-3, atol=1e-4), float((x - y).abs().max())
     assert abs(gna - gnb) <= 1e-3 * max(1.0, gnb)
+
+
+def test_captured_update_is_dropped_when_what_it_baked_in_changes(tmp_path):
+    """The captured minibatch update holds raw pointers to the optimizer's state tensors and bakes lr / clip /
+    coefficients in as kernel scalars.  load_model() swaps the state tensors and a callback may anneal a coefficient:
+    both must invalidate the graph, and training after a load must continue exactly like an agent that never captured."""
+    from shogidrl_b200.core import ActorCritic, PPOAgent
+    dev = torch.device("cuda:0")
+    B, mbs = 1024, 256
+    g = torch.Generator(device="cpu").manual_seed(0)
+    mask = (torch.rand(B, 13536, generator=g) < 0.004)
+    mask[:, 0] = True
+    batch = {"obs": torch.rand(B, 46, 9, 9, generator=g).to(dev), "actions": torch.zeros(B, dtype=torch.int64, device=dev),
+             "log_probs": torch.full((B,), -3.0, device=dev), "values": torch.zeros(B, device=dev),
+             "advantages": torch.randn(B, generator=g).to(dev), "returns": torch.randn(B, generator=g).to(dev),
+             "legal_masks": mask.to(dev)[:, :13527]}
+
+    class Buf:
+        def get_batch(self):
+            return batch
+
+    def make(graph):
+        cfg = make_config(device="cuda", ppo_epochs=2, minibatch_size=mbs, steps_per_epoch=B)
+        cfg.training.cuda_graph_update = graph
+        torch.manual_seed(3)
+        return PPOAgent(ActorCritic(46, 13527), cfg, dev, use_mixed_precision=True)
+
+    a, b = make(True), make(False)
+    for ag in (a, b):
+        ag.learn(Buf()); ag.learn(Buf())
+    assert a._graph is not None
+    ck = str(tmp_path / "ck.pth")
+    a.save_model(ck, 10, 1)
+    # the file is what the reference writes: non-capturable Adam state with a CPU fp32 step counter
+    sd = torch.load(ck, map_location="cpu", weights_only=False)["optimizer_state_dict"]
+    assert sd["param_groups"][0]["capturable"] is False
+    assert all(st["step"].device.type == "cpu" and st["step"].dtype == torch.float32 for st in sd["state"].values())
+    old_state = [t.data_ptr() for st in a.optimizer.state.values() for t in st.values() if torch.is_tensor(t)]
+    for ag in (a, b):
+        assert "error" not in ag.load_model(ck)
+    assert a._graph is None  # dropped: its kernels pointed at the replaced exp_avg / exp_avg_sq / step tensors
+    new_state = [t.data_ptr() for st in a.optimizer.state.values() for t in st.values() if torch.is_tensor(t)]
+    assert old_state != new_state
+    ma, mb_ = a.learn(Buf()), b.learn(Buf())
+    a.learn(Buf()); b.learn(Buf())
+    assert a._graph is not None
+    for k in ma:
+        assert abs(ma[k] - mb_[k]) <= 1e-3 * max(1.0, abs(mb_[k])), (k, ma[k], mb_[k])
+    for x, y in zip(a.model.parameters(), b.model.parameters()):
+        assert torch.allclose(x, y, rtol=1e-3, atol=1e-4)
+    # the moments the checkpoint now holds are the ones the updates since the load have advanced
+    for (pa, sa), (pb, sb) in zip(a.optimizer.state.items(), b.optimizer.state.items()):
+        assert float(sa["step"]) == float(sb["step"]) and torch.allclose(sa["exp_avg"], sb["exp_avg"], rtol=1e-3, atol=1e-6)
+    # an annealed coefficient takes effect on the next learn() (it is a baked scalar of the captured kernels)
+    a.entropy_coef = b.entropy_coef = 0.5
+    key_before = a._graph_key
+    ma, mb_ = a.learn(Buf()), b.learn(Buf())
+    assert a._graph_key != key_before
+    for x, y in zip(a.model.parameters(), b.model.parameters()):
+        assert torch.allclose(x, y, rtol=1e-3, atol=1e-4)
 
 
 @pytest.mark.parametrize("model_kind", ["cnn", "resnet"])
@@ -563,3 +626,65 @@ def test_host_pipelined_env_equals_one_batch():
         for t in range(T):
             assert torch.equal(torch.cat([got[g][t] for g in range(G)]), rewards[t].cpu())
         assert all(int(e.errors().abs().sum()) == 0 for e in pipe.envs)
+
+
+def test_rule_queries_match_oracle_on_random_endgames():
+    """The facade's rule queries, which the hot loop never calls but displays and tests do -- generate_piece_potential_moves
+    (kz_piece_targets), ShogiGame.is_uchi_fu_zume, can_drop_piece, get_king_legal_moves (shogi_game.py:208-260;
+    shogi_rules_logic.py:82-208, 275-359, 424-483) -- against the oracle's restatement of the same reference functions:
+    pseudo-legal targets of EVERY piece of 4,096 random drop-heavy endgames in batch, and the three scalar queries on 256
+    of them (every pawn-drop square in front of a king, sampled drops of every type in hand, both kings)."""
+    from tests.helpers import random_endgames
+    from shogidrl_b200 import VecShogiEnv
+    from shogidrl_b200.shogi import Color, Piece, PieceType, ShogiGame
+
+    dev = torch.device("cuda:0")
+    n = 4096
+    boards, hands, sides, mcs = random_endgames(n, 2024)
+    games = [orc.OracleGame.from_arrays(boards[i], hands[i], int(sides[i]), 0, 500, evaluate_termination=False) for i in range(n)]
+    env = VecShogiEnv(n, device=dev, auto_reset=False)
+    env.load_positions(boards, hands, sides, mcs, eval_termination=False)
+    checked = 0
+    for sq in range(81):
+        occ = np.nonzero(boards[:, sq])[0]
+        if len(occ) == 0:
+            continue
+        w = env.piece_targets(np.full(n, sq, np.int32)).cpu().numpy().astype(np.uint32)
+        got = ((w[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(n, 96)[:, :81].astype(np.uint8)
+        for i in occ:
+            want = games[i].piece_targets(sq)
+            assert np.array_equal(got[i], want), (i, sq, int(boards[i, sq]))
+            checked += 1
+    assert checked > 20000
+    # scalar facade queries
+    rng = np.random.default_rng(5)
+    game = ShogiGame()
+    ufz_true = drops = 0
+    for i in range(256):
+        game.board = [[Piece.from_code(int(boards[i, r * 9 + c])) for c in range(9)] for r in range(9)]
+        for color in (0, 1):
+            for t in range(7):
+                game.hands[color][PieceType(t)] = int(hands[i, color * 7 + t])
+        game.current_player = Color(int(sides[i]))
+        game.move_count = 0
+        game.game_over, game.winner, game.termination_reason = False, None, None
+        o = games[i]
+        for color in (Color.BLACK, Color.WHITE):
+            assert game.get_king_legal_moves(color) == o.king_legal_moves(color.value), (i, color)
+            # the square in front of the enemy king (where a pawn drop can give check) + two random squares
+            ek = game.find_king(color.opponent())
+            cand = [int(x) for x in rng.integers(0, 81, 2)]
+            if ek is not None:
+                fr = ek[0] + (1 if color == Color.BLACK else -1)
+                if 0 <= fr < 9:
+                    cand.append(fr * 9 + ek[1])
+            for sq in cand:
+                want = o.is_uchi_fu_zume(sq, color.value)
+                assert game.is_uchi_fu_zume(sq // 9, sq % 9, color) == want, (i, color, sq)
+                ufz_true += int(want)
+            for t in range(7):
+                for sq in [int(x) for x in rng.integers(0, 81, 2)] + cand[-1:]:
+                    want = o.can_drop(t, sq, color.value)
+                    assert game.can_drop_piece(PieceType(t), sq // 9, sq % 9, color) == want, (i, color, t, sq)
+                    drops += int(want)
+    assert drops > 500

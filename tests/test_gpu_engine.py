@@ -13,6 +13,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import oracle as orc  # noqa: E402  (checker only)
+from tests.helpers import random_endgames as _random_endgames  # noqa: E402
 
 
 def _digest(obs_row: np.ndarray) -> int:
@@ -329,47 +330,6 @@ def test_illegal_actions_set_error_bits():
     assert int(out["done"].sum()) == 0 and float(out["reward"].abs().sum()) == 0.0
 
 
-def _random_endgames(n, seed):
-    """Drop-heavy endgame positions: two kings, a few random pieces, pieces in both hands (BASELINE config 5's
-    'drops-heavy endgames').  Filtered with the oracle so that the side not to move is not in check and the
-    side to move has a legal move."""
-    rng = np.random.default_rng(seed)
-    boards, hands, sides = [], [], []
-    types = [0, 0, 0, 1, 2, 3, 4, 4, 5, 6, 8, 9, 10, 11, 12, 13]
-    while len(boards) < n:
-        b = np.zeros(81, np.int8)
-        k0, k1 = rng.choice(81, 2, replace=False)
-        if max(abs(k0 // 9 - k1 // 9), abs(k0 % 9 - k1 % 9)) < 2:
-            continue
-        b[k0], b[k1] = 8, 22
-        for color in (0, 1):
-            for _ in range(int(rng.integers(0, 6))):
-                sq = int(rng.integers(0, 81))
-                t = int(rng.choice(types))
-                r = sq // 9
-                if b[sq] != 0:
-                    continue
-                last, second = (0, 1) if color == 0 else (8, 7)
-                if t in (0, 1) and r == last:
-                    continue
-                if t == 2 and r in (last, second):
-                    continue
-                if t == 0 and any(b[rr * 9 + sq % 9] == 1 + 14 * color for rr in range(9)):
-                    continue
-                b[sq] = 1 + t + 14 * color
-        h = np.zeros(14, np.uint8)
-        for color in (0, 1):
-            h[color * 7 + 0] = rng.integers(0, 5)
-            for t in range(1, 7):
-                h[color * 7 + t] = rng.integers(0, 3) if rng.random() < 0.5 else 0
-        side = int(rng.integers(0, 2))
-        g = orc.OracleGame.from_arrays(b, h, side, 0, 500, evaluate_termination=False)
-        if g.in_check(1 - side) or len(g.legal_indices()) == 0:
-            continue
-        boards.append(b); hands.append(h); sides.append(side)
-    return np.stack(boards), np.stack(hands), np.asarray(sides, np.uint8), np.zeros(n, np.int32)
-
-
 def test_selfplay_from_drop_heavy_endgames():
     """Step-mode parity from drop-heavy endgames: exercises the specialised uchifuzume test, drops that answer
     checks, promoted sliders, and auto-reset back to the start position."""
@@ -542,6 +502,52 @@ def test_full_size_stress_properties():
     assert torch.equal(env.obs, obs_k) and torch.equal(env.mask, mask_k)       # refresh == what the step kernel wrote
     r = reasons.tolist()
     assert r[1] > 0 and r[3] > 0 and r[4] > 0, r                               # checkmates, truncations and sennichite all occur
+
+
+def test_config5_full_size():
+    """BASELINE config 5 at its stated per-GPU shape -- 262,144 games, max_moves 500, the 1/3 hirate / 1/3 drops-heavy
+    endgames / 1/3 4-ply-cycle start mix that ``bench.py --workload cfg5`` runs -- stepped for 520 plies with random legal
+    play, so that every kind of ending occurs: checkmates, 500-ply truncations, sennichite (all scripted games exactly on
+    ply 13).  A sample of 4,096 games of THIS batch (2,048 hirate + 2,048 endgame starts, each keyed by its own position
+    in the batch) is replayed by the oracle: per-step termination reasons, hence the histogram, must be identical."""
+    import bench
+    from shogidrl_b200 import VecShogiEnv
+    from shogidrl_b200.utils import move_to_index
+
+    dev = torch.device("cuda:0")
+    n, T, seed, k = 262144, 520, 1234, 2048
+    boards, hands, sides, mcs, (n_h, n_e, n_c) = bench.cfg5_positions(n)
+    assert n_h + n_e + n_c == n and min(n_h, n_e, n_c) >= n // 3
+    env = VecShogiEnv(n, max_moves_per_game=500, device=dev, seed=seed, auto_reset=True)
+    assert env.state_bytes < 5 * 2 ** 30  # 4.3 GB of state: 500-ply repetition tables for 262,144 games
+    env.load_positions(boards, hands, sides, mcs, eval_termination=False)
+    env.step_index = 0
+    acts = [torch.zeros(n, dtype=torch.int64, device=dev) for _ in range(2)]
+    env.refresh(random_actions=True, next_out=acts[0])
+    cycle = [move_to_index(m) for m in bench.CYCLE_MOVES]
+    blocks = [(0, k), (n_h, n_h + k)]  # the sampled games: first 2,048 hirate starts, first 2,048 endgame starts
+    sample = torch.cat([torch.arange(a, b, device=dev) for a, b in blocks])
+    reasons = torch.zeros((T, sample.numel()), dtype=torch.uint8, device=dev)
+    hist = torch.zeros(5, dtype=torch.int64, device=dev)
+    for t in range(T):
+        a = acts[t & 1]
+        if t < 13:
+            a[n_h + n_e:] = cycle[t % 4]
+        out = env.step(a, random_actions=True, next_out=acts[(t + 1) & 1])
+        reasons[t] = out["reason"][sample]
+        hist += torch.bincount(out["reason"].long(), minlength=5)
+        if t < 13:
+            want = 4 if t == 12 else 0
+            assert bool((out["reason"][n_h + n_e:] == want).all()), t  # sennichite exactly on the 13th ply, all 87,381 games
+    assert int(env.errors().abs().sum()) == 0
+    h = hist.tolist()
+    assert h[1] > 0 and h[3] > 0 and h[4] >= n_c, h  # Tsumi, max-moves and sennichite all occur
+    got = reasons.cpu().numpy()
+    for j, (a, b) in enumerate(blocks):
+        ref = orc.selfplay(b - a, T, env0=a, max_moves=500, seed=seed, threads=os.cpu_count() or 1, want_final=False,
+                           start=(boards[a:b], hands[a:b], sides[a:b], mcs[a:b]))
+        assert np.array_equal(got[:, j * k:(j + 1) * k], ref["reasons"]), j
+        assert np.bincount(ref["reasons"].ravel(), minlength=5)[1:].sum() > 0
 
 
 def test_storage_and_action_validation_on_a_live_env():

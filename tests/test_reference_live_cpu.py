@@ -98,3 +98,100 @@ def test_experience_buffer_host_semantics(ref):
     ours.clear()
     theirs.clear()
     assert len(ours) == len(theirs) == 0
+
+
+def test_checkpoint_written_here_resumes_in_the_reference_on_cpu(ref, tmp_path):
+    """PPOAgent.save_model writes the reference's checkpoint dictionary (ppo_agent.py:462-487) with the optimizer state
+    the reference's own Adam writes -- capturable False, `step` a CPU fp32 tensor -- so the reference's
+    PPOAgent.load_model + learn() resumes from it on a CPU-only host (torch's Adam asserts that capturable state lives
+    on CUDA).  Built here on CPU with the state laid out the way the fused CUDA tail keeps it."""
+    import copy
+    from types import SimpleNamespace
+
+    from keisei.core.experience_buffer import ExperienceBuffer as RBuffer
+    from keisei.core.neural_network import ActorCritic as RActorCritic
+    from keisei.core.ppo_agent import PPOAgent as RAgent
+
+    from shogidrl_b200.core import ActorCritic, PPOAgent
+    from tests.helpers import make_config
+
+    cfg = make_config(device="cpu", ppo_epochs=1, minibatch_size=8, steps_per_epoch=8)
+    torch.manual_seed(0)
+    agent = PPOAgent(ActorCritic(46, 13527), cfg, torch.device("cpu"))
+    for p in agent.model.parameters():  # optimizer state as kz_adam_clip_step keeps it: tensors, step as fp32 scalar tensor
+        agent.optimizer.state[p] = {"step": torch.tensor(3.0), "exp_avg": torch.full_like(p, 1e-3),
+                                    "exp_avg_sq": torch.full_like(p, 1e-6)}
+    agent.optimizer.param_groups[0]["capturable"] = True  # what the CUDA agent's optimizer carries
+    path = str(tmp_path / "ck.pth")
+    agent.save_model(path, 123, 4, {"black_wins": 2, "white_wins": 1, "draws": 1})
+
+    class Cfg(SimpleNamespace):
+        def model_copy(self, deep=True):
+            return copy.deepcopy(self)
+
+    rcfg = Cfg(env=Cfg(**vars(cfg.env)), training=Cfg(**vars(cfg.training)))
+    ragent = RAgent(RActorCritic(46, 13527), rcfg, torch.device("cpu"))
+    out = ragent.load_model(path)
+    assert out.get("global_timestep") == 123 and out.get("black_wins") == 2 and "error" not in out
+    for (k, a), (_, b) in zip(agent.model.state_dict().items(), ragent.model.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert ragent.optimizer.param_groups[0]["capturable"] is False
+    # and the reference trains on from it
+    buf = RBuffer(8, 0.99, 0.95, "cpu")
+    mask = torch.zeros(13527, dtype=torch.bool)
+    mask[:30] = True
+    for t in range(8):
+        buf.add(torch.rand(46, 9, 9), t, 0.1 * t, -3.0, 0.0, t == 7, mask)
+    buf.compute_advantages_and_returns(0.0)
+    m = ragent.learn(buf)
+    assert all(np.isfinite(v) for v in m.values())
+    st = next(iter(ragent.optimizer.state.values()))
+    assert float(st["step"]) == 4.0  # continued from the saved step count
+
+
+def test_oracle_rule_queries_match_the_reference(ref):
+    """The oracle's restatements of generate_piece_potential_moves, is_uchi_fu_zume, can_drop_piece and
+    get_king_legal_moves -- the checker of tests/test_gpu_api.py::test_rule_queries_match_oracle_on_random_endgames --
+    against the reference's own methods on drop-heavy endgames and on the uchifuzume known-answer positions."""
+    from oracle import oracle as orc
+    from tests.helpers import random_endgames
+    rshogi = ref["shogi"]
+    Color, PieceType, Piece = rshogi.Color, rshogi.PieceType, rshogi.Piece
+    boards, hands, sides, _ = random_endgames(24, 31)
+    sfens = ["7gk/9/7GP/9/9/9/9/9/K8 b P 1", "8k/9/8P/9/9/9/9/9/K8 b P 1", "6R1k/9/7G1/9/9/9/9/9/K8 b P 1",
+             "k8/9/1G7/9/9/9/9/9/K7R b P 1"]
+    cases = [orc.OracleGame.from_arrays(boards[i], hands[i], int(sides[i]), 0, 500, evaluate_termination=False) for i in range(24)]
+    cases += [orc.OracleGame.from_sfen(s, evaluate_termination=False) for s in sfens]
+    rng = random.Random(3)
+    ufz = 0
+    for o in cases:
+        b, h, m = o.export()
+        g = rshogi.ShogiGame()
+        g.board = [[None] * 9 for _ in range(9)]
+        for sq in range(81):
+            if b[sq]:
+                g.board[sq // 9][sq % 9] = Piece(PieceType((int(b[sq]) - 1) % 14), Color((int(b[sq]) - 1) // 14))
+        for color in (0, 1):
+            for t in range(7):
+                g.hands[color][PieceType(t)] = int(h[color * 7 + t])
+        g.current_player = Color(int(m[0]))
+        for sq in range(81):
+            p = g.board[sq // 9][sq % 9]
+            if p is not None:
+                want = np.zeros(81, np.uint8)
+                for (r, c) in g.get_individual_piece_moves(p, sq // 9, sq % 9):
+                    want[r * 9 + c] = 1
+                assert np.array_equal(o.piece_targets(sq), want), sq
+        for color in (Color.BLACK, Color.WHITE):
+            assert o.king_legal_moves(color.value) == g.get_king_legal_moves(color)
+            squares = [rng.randrange(81) for _ in range(4)]
+            ek = g.find_king(color.opponent())
+            if ek is not None and 0 <= ek[0] + (1 if color == Color.BLACK else -1) < 9:
+                squares.append((ek[0] + (1 if color == Color.BLACK else -1)) * 9 + ek[1])
+            for sq in squares:
+                want = bool(g.is_uchi_fu_zume(sq // 9, sq % 9, color))
+                assert o.is_uchi_fu_zume(sq, color.value) == want, (sq, color)
+                ufz += int(want)
+                for t in range(7):
+                    assert o.can_drop(t, sq, color.value) == bool(g.can_drop_piece(PieceType(t), sq // 9, sq % 9, color)), (t, sq)
+    assert ufz >= 1  # the known-answer uchifuzume position is among the cases
