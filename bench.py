@@ -780,7 +780,7 @@ def measure_ppo(args, dev, world, rank, barrier):
     else:
         model = ActorCritic(46, 13527)
     tr = SelfPlayTrainer(model, cfg, N, T, dev, use_mixed_precision=True)
-    for _ in range(max(1, args.ppo_warmup)):
+    for _ in range(max(2, args.ppo_warmup)):  # epoch 1 captures the update graph, epoch 2 the rollout graph
         tr.run_epoch()
     barrier()
     sampler = ClockSampler(dev.index or 0)
@@ -852,7 +852,7 @@ def measure_ppo(args, dev, world, rank, barrier):
         cnn = args.ppo_model == "cnn"
         rb = rollout_bytes_per_sample(mean_ply)
         rec = {"metric": "PPO self-play samples/sec", "value": samples / (total_ms * 1e-3), "unit": "samples/s",
-               "n_gpus": world, "steps": steps, "warmup": max(1, args.ppo_warmup), "ms_per_step": total_ms / steps,
+               "n_gpus": world, "steps": steps, "warmup": max(2, args.ppo_warmup), "ms_per_step": total_ms / steps,
                "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
                "config": {"workload": f"BASELINE config {3 if cnn else 4}: PPO self-play, {args.ppo_model} policy-value net "
                                       f"(bf16 autocast), {N} envs/GPU, T={T}, fused masked sampling on legal bitmaps + device "
@@ -946,7 +946,7 @@ def main():
     ap.add_argument("--ref-same-minibatch", action="store_true", help="--impl reference --workload ppo: minibatch = min(--ppo-minibatch, steps) instead of the reference's 64")
     ap.add_argument("--no-ppo", action="store_true", help="skip the PPO (config 3) record of the default workload")
     ap.add_argument("--ppo-steps", type=int, default=2, help="timed PPO epochs of the `ppo` record")
-    ap.add_argument("--ppo-warmup", type=int, default=1, help="untimed PPO epochs (the first also captures the update graph)")
+    ap.add_argument("--ppo-warmup", type=int, default=2, help="untimed PPO epochs (the first captures the update graph, the second the rollout graph)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -31,6 +31,7 @@ extern "C" {
 #define KZ_MASK_PAD_STRIDE 13536 /* 16-byte multiple >= 13527: fast-path row stride */
 #define KZ_BITMAP_WORDS 448     /* row of a legal BITMAP: bit i = action i legal; 423 words used, zero-padded to 14 per lane */
 #define KZ_BITMAP_WORDS_MIN 423 /* smallest row stride (in 32-bit words) the bitmap readers accept */
+#define KZ_COBS_WORDS 40        /* compact observation: 84 bytes of plane indices + 18 fp32 constant-plane values + pad = 160 B */
 
 /* termination reason codes (shogi_core_definitions.py:135-147) */
 #define KZ_ONGOING 0
@@ -131,9 +132,9 @@ int kz_step(void* state, int n, int hist_cap, const void* actions, int actions_i
  * mask != NULL: byte-mask form (kz_step); bitmap != NULL: rollout form (kz_step_rollout); not both. */
 int kz_step_range(void* state, int n, int hist_cap, int first, int count, int counter_slot, const void* actions,
                   int actions_i64, float* obs, int64_t obs_stride, uint8_t* mask, int64_t mask_stride, uint32_t* bitmap,
-                  int64_t bitmap_stride_words, float* reward, uint8_t* done, uint8_t* reason, int8_t* winner, int32_t* ep_len,
-                  int32_t* legal_count, void* next_actions, uint64_t seed, uint32_t rng_step, uint32_t env_offset,
-                  int auto_reset, void* stream);
+                  int64_t bitmap_stride_words, uint32_t* cobs, float* reward, uint8_t* done, uint8_t* reason, int8_t* winner,
+                  int32_t* ep_len, int32_t* legal_count, void* next_actions, uint64_t seed, uint32_t rng_step,
+                  uint32_t env_offset, int auto_reset, void* stream);
 
 /* Split pipeline (experimental; same results as kz_step, bit for bit): kz_step_compact is kz_step without the two row
  * outputs -- it leaves the successor's 13,527-bit legal bitmap in bitmap [n][448] uint32 (bit i of the row = action i;
@@ -154,13 +155,19 @@ int kz_expand(const void* state, int n, int hist_cap, const uint32_t* bitmap, fl
  * (utils.py:310-336) marks -- instead of the 13,527-byte mask row: 1,792 B instead of 13,536 B written per game here, and
  * read again by kz_sample_bitmap and by every kz_eval_bitmap_* pass of the update.  obs as in kz_step (optional).
  * kz_legal_bitmap is the kz_refresh counterpart (current positions, no move); kz_bitmap_expand turns bitmap rows into
- * byte-mask rows for callers of the reference API (ExperienceBuffer.legal_masks, experience_buffer.py:52-54). */
+ * byte-mask rows for callers of the reference API (ExperienceBuffer.legal_masks, experience_buffer.py:52-54).
+ * cobs (optional, [n][KZ_COBS_WORDS] uint32): the COMPACT OBSERVATION of the returned state -- the same information as
+ * the 46x9x9 tensor of generate_neural_network_observation (shogi_game_io.py:434-539) in 160 bytes: bytes 0..80 = for
+ * each observation square (row-major, already rotated 180 degrees when White is to move) the index 0..27 of the one
+ * piece plane that is 1.0 there, 0xFF if none; words 21..38 = the fp32 values of the constant planes 28..45 (hands / 18,
+ * side to move, move_count / max_moves, two reserved zeros).  kz_cobs_conv_fwd / _wgrad consume it. */
 int kz_step_rollout(void* state, int n, int hist_cap, const void* actions, int actions_i64, float* obs,
-                    int64_t obs_stride, uint32_t* bitmap, int64_t bitmap_stride_words, float* reward, uint8_t* done,
-                    uint8_t* reason, int8_t* winner, int32_t* ep_len, int32_t* legal_count, void* next_actions,
-                    uint64_t seed, uint32_t rng_step, uint32_t env_offset, int auto_reset, void* stream);
+                    int64_t obs_stride, uint32_t* bitmap, int64_t bitmap_stride_words, uint32_t* cobs, float* reward,
+                    uint8_t* done, uint8_t* reason, int8_t* winner, int32_t* ep_len, int32_t* legal_count,
+                    void* next_actions, uint64_t seed, uint32_t rng_step, uint32_t env_offset, int auto_reset,
+                    void* stream);
 int kz_legal_bitmap(void* state, int n, int hist_cap, float* obs, int64_t obs_stride, uint32_t* bitmap,
-                    int64_t bitmap_stride_words, int32_t* legal_count, void* stream);
+                    int64_t bitmap_stride_words, uint32_t* cobs, int32_t* legal_count, void* stream);
 int kz_bitmap_expand(const uint32_t* bitmap, int64_t bitmap_stride_words, const int64_t* bitmap_rows, int n, uint8_t* mask,
                      int64_t mask_stride, void* stream);
 
@@ -184,15 +191,17 @@ int kz_errors(void* state, int n, int hist_cap, int32_t* out, int clear, void* s
  *   logp fp32; entropy optional fp32.  Rows whose mask is all zero fall back to the uniform
  *   distribution over all actions (base_actor_critic.py:93-101).  Sampling is inverse-CDF on a
  *   counter-based uniform keyed (seed, offset + row): statistical, not bitwise, parity with
- *   torch.multinomial. */
+ *   torch.multinomial.  offset_dev (optional device uint64): added to offset when the kernel runs,
+ *   so that a launch captured in a CUDA graph draws fresh numbers on every replay (the caller
+ *   advances the device counter between launches). */
 int kz_sample_masked(const void* logits, int logits_bf16, int64_t ld, const uint8_t* mask, int64_t ldm,
-                     int n, uint64_t seed, uint64_t offset, void* actions, int actions_i64, float* logp,
-                     float* entropy, int deterministic, void* stream);
+                     int n, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* actions,
+                     int actions_i64, float* logp, float* entropy, int deterministic, void* stream);
 /* The same with the legal set given as bitmap rows (kz_step_rollout): bitmap [n][ldb_words] uint32.  For a 16-byte
  * aligned byte mask of the same set the two entry points return identical actions, log-probs and entropies. */
 int kz_sample_bitmap(const void* logits, int logits_bf16, int64_t ld, const uint32_t* bitmap, int64_t ldb_words,
-                     int n, uint64_t seed, uint64_t offset, void* actions, int actions_i64, float* logp,
-                     float* entropy, int deterministic, void* stream);
+                     int n, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* actions,
+                     int actions_i64, float* logp, float* entropy, int deterministic, void* stream);
 
 /* ExperienceBuffer.compute_advantages_and_returns (experience_buffer.py:99-145) over a [T][N]
  * layout, one reverse scan per env column (N = 1 is the reference's flat buffer):
@@ -260,6 +269,17 @@ int kz_obs_conv_fwd(const float* obs, const int64_t* obs_rows, const float* weig
 int kz_obs_conv_wgrad_ctas(int n);
 int kz_obs_conv_wgrad(const float* obs, const int64_t* obs_rows, const void* y_bf16, const void* dout, int dout_bf16,
                       int cout, int n, float* workspace, int ctas, float* dweight, float* dbias, void* stream);
+
+/* The same layer fed with the engine's COMPACT OBSERVATIONS (kz_step_rollout's cobs output, [..][KZ_COBS_WORDS] uint32; row
+ * cobs_rows[b] or b) instead of the fp32 tensors they summarise -- 160 bytes per board instead of 14,904.  The forward needs
+ * no dense product: at most one of the 28 piece planes is non-zero per square, so an output is the bias + nine weight
+ * look-ups + the constant planes' contribution; the weight gradient patches its board tile from one board to the next.
+ * Same operand rounding (bf16) and fp32 accumulation as kz_obs_conv_*; valid for observations the engine produced. */
+int kz_cobs_conv_fwd(const uint32_t* cobs, const int64_t* cobs_rows, const float* weight, const float* bias, int cout, int n,
+                     int relu, void* out_bf16, void* stream);
+int kz_cobs_conv_wgrad_ctas(int n); /* workspace = ctas * 16 * 432 floats, as for kz_obs_conv_wgrad */
+int kz_cobs_conv_wgrad(const uint32_t* cobs, const int64_t* cobs_rows, const void* y_bf16, const void* dout, int dout_bf16,
+                       int cout, int n, float* workspace, int ctas, float* dweight, float* dbias, void* stream);
 
 /* ---- tail of a PPO minibatch update: torch.nn.utils.clip_grad_norm_(parameters, max_norm) followed by
  * torch.optim.Adam.step() (keisei/core/ppo_agent.py:405-413, optimizer built at :66-80), fused: one read of every

@@ -64,6 +64,10 @@ report("kz_obs_conv_fwd (rows gather)", timed(lambda: nn_ops.obs_conv(flat_obs, 
 y = nn_ops.obs_conv(flat_obs, w, b, relu=True, rows=rows)
 dy = torch.randn_like(y)
 report("kz_obs_conv_wgrad (+reduce)", timed(lambda: torch.autograd.grad(y, (w, b), dy, retain_graph=True)), N * (14904 + 2 * 2592))
+flat_cobs = buf.cobs[:T].reshape(N * T, 40)
+report("kz_cobs_conv_fwd (rows gather)", timed(lambda: nn_ops.obs_conv(flat_obs, w, b, relu=True, rows=rows, cobs=flat_cobs)), N * (160 + 2592))
+yc = nn_ops.obs_conv(flat_obs, w, b, relu=True, rows=rows, cobs=flat_cobs)
+report("kz_cobs_conv_wgrad (+reduce)", timed(lambda: torch.autograd.grad(yc, (w, b), dy, retain_graph=True)), N * (160 + 2 * 2592))
 for p in agent.model.parameters():
     p.grad = torch.randn_like(p) * 1e-3
 nparam = sum(p.numel() for p in agent.model.parameters())

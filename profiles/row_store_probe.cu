@@ -35,8 +35,14 @@ __global__ void __launch_bounds__(256) probe(uint8_t* mask, float* obs, int n, i
   __shared__ uint32_t s_bm[8][448];   // so the mask image has its own array)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (mode & 32) {
-    const size_t total = (size_t)n * (MASK_STRIDE + OBS_FLOATS * 4) / 1024;
     uint8_t* base = mask;  // the two buffers are one allocation
+    if (mode & 512) {  // 128-bit stores: 512 B per warp instruction
+      const size_t total = (size_t)n * (MASK_STRIDE + OBS_FLOATS * 4) / 512;
+      for (size_t i = (size_t)blockIdx.x * 8 + warp; i < total; i += (size_t)gridDim.x * 8)
+        reinterpret_cast<uint4*>(base + i * 512)[lane] = make_uint4(0, 0, 0, 0);
+      return;
+    }
+    const size_t total = (size_t)n * (MASK_STRIDE + OBS_FLOATS * 4) / 1024;
     for (size_t i = (size_t)blockIdx.x * 8 + warp; i < total; i += (size_t)gridDim.x * 8) st_zero256(base + i * 1024 + lane * 32);
     return;
   }
@@ -202,6 +208,13 @@ __global__ void __launch_bounds__(256) probe(uint8_t* mask, float* obs, int n, i
   }
 }
 
+__global__ void __launch_bounds__(128) fill_np(uint4* p, size_t n16) {  // non-persistent: 4 x 16 B per thread, like an elementwise fill
+  const size_t i0 = ((size_t)blockIdx.x * 128 + threadIdx.x);
+  const size_t stride = (size_t)gridDim.x * 128;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { const size_t i = i0 + k * stride; if (i < n16) p[i] = make_uint4(0, 0, 0, 0); }
+}
+
 int main() {
   const int n = 65536;
   uint8_t* buf;
@@ -211,8 +224,8 @@ int main() {
   float* obs = reinterpret_cast<float*>(buf + mask_bytes);
   int sms;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  const int modes[] = {32, 1, 2, 3, 3 | 4, 3 | 8, 3 | 4 | 8, 1 | 16, 1 | 4 | 16, 64 | 16, 64, 16, 128, 128 | 256};
-  const char* names[] = {"flat fill (reference)", "mask fill", "obs fill", "mask+obs fill", "fill + mask sparse", "fill + obs sparse",
+  const int modes[] = {32, 32 | 512, 1, 2, 3, 3 | 4, 3 | 8, 3 | 4 | 8, 1 | 16, 1 | 4 | 16, 64 | 16, 64, 16, 128, 128 | 256};
+  const char* names[] = {"flat fill (reference)", "flat fill, 128-bit stores", "mask fill", "obs fill", "mask+obs fill", "fill + mask sparse", "fill + obs sparse",
                          "fill + both sparse (= kz_step's writers)", "mask fill + obs ONCE", "mask fill+sparse + obs ONCE",
                          "mask ONCE + obs ONCE", "mask ONCE only", "obs ONCE only", "CTA-cooperative tile, composed ONCE",
                          "CTA-cooperative tile, zeros"};
@@ -243,6 +256,22 @@ int main() {
       printf("%9.4f", ms);
     }
     printf("   %.0f GB/s  (%s)\n", bytes / best / 1e6, cudaGetErrorString(cudaGetLastError()));
+  }
+  {  // non-persistent elementwise-style fill of the same bytes
+    const size_t n16 = (mask_bytes + obs_bytes) / 16;
+    const unsigned grid = (unsigned)((n16 + 511) / 512);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 3; i++) fill_np<<<grid, 128>>>(reinterpret_cast<uint4*>(buf), n16);
+    cudaEventRecord(e0);
+    for (int i = 0; i < 10; i++) fill_np<<<grid, 128>>>(reinterpret_cast<uint4*>(buf), n16);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= 10;
+    printf("%-44s%9.4f   %.0f GB/s  (non-persistent grid of %u CTAs x 128 threads x 64 B)\n", "flat fill, elementwise-style", ms,
+           (double)(mask_bytes + obs_bytes) / ms / 1e6, grid);
   }
   return 0;
 }

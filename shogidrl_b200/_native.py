@@ -25,8 +25,10 @@ EXPORTS = [
     "kz_gae", "kz_gae_exact", "kz_eval_masked_fwd", "kz_eval_masked_bwd", "kz_obs_conv_fwd", "kz_obs_conv_wgrad_ctas",
     "kz_obs_conv_wgrad", "kz_ppo_loss", "kz_eval_masked_bwd_bias", "kz_adam_clip_workspace", "kz_adam_clip_step",
     "kz_step_compact", "kz_expand", "kz_step_rollout", "kz_legal_bitmap", "kz_bitmap_expand", "kz_sample_bitmap",
-    "kz_eval_bitmap_fwd", "kz_eval_bitmap_bwd", "kz_step_range",
+    "kz_eval_bitmap_fwd", "kz_eval_bitmap_bwd", "kz_step_range", "kz_cobs_conv_fwd", "kz_cobs_conv_wgrad_ctas",
+    "kz_cobs_conv_wgrad",
 ]
+COBS_WORDS = 40
 ABI_VERSION = 2
 
 
@@ -61,19 +63,22 @@ def lib() -> C.CDLL:
     L.kz_step.argtypes = [vp, i32, i32, vp, i32, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, vp]
     L.kz_step_compact.argtypes = [vp, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, vp]
     L.kz_expand.argtypes = [vp, i32, i32, vp, vp, i64, vp, i64, vp]
-    L.kz_step_rollout.argtypes = [vp, i32, i32, vp, i32, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, vp]
-    L.kz_step_range.argtypes = [vp, i32, i32, i32, i32, i32, vp, i32, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp,
+    L.kz_step_rollout.argtypes = [vp, i32, i32, vp, i32, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, vp]
+    L.kz_step_range.argtypes = [vp, i32, i32, i32, i32, i32, vp, i32, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp,
                                 u64, u32, u32, i32, vp]
-    L.kz_legal_bitmap.argtypes = [vp, i32, i32, vp, i64, vp, i64, vp, vp]
+    L.kz_legal_bitmap.argtypes = [vp, i32, i32, vp, i64, vp, i64, vp, vp, vp]
+    L.kz_cobs_conv_fwd.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp]
+    L.kz_cobs_conv_wgrad_ctas.argtypes = [i32]
+    L.kz_cobs_conv_wgrad.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, i32, vp, vp, vp]
     L.kz_bitmap_expand.argtypes = [vp, i64, vp, i32, vp, i64, vp]
-    L.kz_sample_bitmap.argtypes = [vp, i32, i64, vp, i64, i32, u64, u64, vp, i32, vp, vp, i32, vp]
+    L.kz_sample_bitmap.argtypes = [vp, i32, i64, vp, i64, i32, u64, u64, vp, vp, i32, vp, vp, i32, vp]
     L.kz_eval_bitmap_fwd.argtypes = [vp, i32, i64, vp, i64, vp, vp, i32, vp, vp, vp, vp]
     L.kz_eval_bitmap_bwd.argtypes = [vp, i32, i64, vp, i64, vp, vp, i32, vp, vp, vp, vp, i64, vp, vp]
     L.kz_legal_mask.argtypes = [vp, i32, i32, vp, i64, vp, vp]
     L.kz_observe.argtypes = [vp, i32, i32, vp, i64, vp]
     L.kz_errors.argtypes = [vp, i32, i32, vp, i32, vp]
     L.kz_piece_targets.argtypes = [vp, i32, i32, vp, vp, vp]
-    L.kz_sample_masked.argtypes = [vp, i32, i64, vp, i64, i32, u64, u64, vp, i32, vp, vp, i32, vp]
+    L.kz_sample_masked.argtypes = [vp, i32, i64, vp, i64, i32, u64, u64, vp, vp, i32, vp, vp, i32, vp]
     L.kz_gae.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp, vp]
     L.kz_gae_exact.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp, vp]
     L.kz_eval_masked_fwd.argtypes = [vp, i32, i64, vp, i64, vp, vp, i32, vp, vp, vp, vp]

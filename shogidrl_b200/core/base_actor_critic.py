@@ -45,11 +45,14 @@ class BaseActorCriticModel(nn.Module):
         raise NotImplementedError("Subclasses must implement forward method")
 
     def get_action_and_value(self, obs: torch.Tensor, legal_mask: Optional[torch.Tensor] = None,
-                             deterministic: bool = False, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+                             deterministic: bool = False, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                             cobs: Optional[torch.Tensor] = None, draw_counter: Optional[torch.Tensor] = None
                              ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """``legal_mask``: bool/uint8 [B, 13527] as in the reference, or the engine's legal bitmap rows (int32
-        [B, 448]).  ``out`` = (actions int64 [B], log_probs fp32 [B]): the sampler writes there (rollout storage)."""
-        logits, value = self.forward(obs)
+        [B, 448]).  ``out`` = (actions int64 [B], log_probs fp32 [B]): the sampler writes there (rollout storage).
+        ``cobs``: the engine's compact observations of ``obs`` (int32 [B, 40]) for models whose input layer reads them."""
+        logits, value = self.forward(obs, cobs=cobs) if cobs is not None and getattr(self, "reads_compact_obs", False) \
+            else self.forward(obs)
         if legal_mask is None:
             legal_mask = torch.ones_like(logits, dtype=torch.bool)
         elif legal_mask.dim() == 1:
@@ -58,10 +61,16 @@ class BaseActorCriticModel(nn.Module):
             legal_mask = legal_mask.expand(logits.shape[0], -1)
         if logits.dtype not in (torch.float32, torch.bfloat16):
             logits = logits.float()
-        n = logits.shape[0]
-        offset = next(_sample_counter) * (1 << 20)
-        action, log_prob, _ = rl.sample_masked(logits, legal_mask, seed=self.sample_seed, offset=offset,
-                                               deterministic=deterministic, out=out)
+        if draw_counter is not None:
+            # the draw counter lives on the device and is advanced by a device op: the whole call can sit in a CUDA graph
+            # and still draw fresh numbers on every replay
+            action, log_prob, _ = rl.sample_masked(logits, legal_mask, seed=self.sample_seed, offset=0,
+                                                   deterministic=deterministic, out=out, offset_tensor=draw_counter)
+            draw_counter.add_(1 << 20)
+        else:
+            offset = next(_sample_counter) * (1 << 20)
+            action, log_prob, _ = rl.sample_masked(logits, legal_mask, seed=self.sample_seed, offset=offset,
+                                                   deterministic=deterministic, out=out)
         if value.dim() > 1 and value.shape[-1] == 1:
             value = value.squeeze(-1)
         return action, log_prob, value
@@ -116,23 +125,49 @@ class ActorCritic(BaseActorCriticModel):
         self.value_head = nn.Linear(16 * 81, 1)
 
     fused_minibatch = True  # forward(obs_store, rows=..., actions=..., legal_mask=...) evaluates a PPO minibatch
+    reads_compact_obs = True  # forward(x, cobs=...) feeds the input layer from the engine's 160-byte compact observations
 
-    def forward(self, x, rows=None, actions=None, legal_mask=None, mask_rows=None):
+    def forward(self, x, rows=None, actions=None, legal_mask=None, mask_rows=None, cobs=None):
         """``forward(x)`` -> (logits, value) as in the reference.  The PPO update calls (through the DDP wrapper when
         there is one) ``forward(obs_store, rows=mb, actions=a, legal_mask=mask_store, mask_rows=mb)`` and gets
         (log_probs, entropy, value) of the minibatch: observations and masks are read in place through the row
         indices, the input layer and the policy head + masked evaluation each run as one fused node."""
         if nn_ops.obs_conv_applicable(self.conv, x):  # bf16 autocast on CUDA: fused input layer (csrc/kz_nn.cu)
-            h = self.flatten(nn_ops.obs_conv(x, self.conv.weight, self.conv.bias, relu=True, rows=rows))
+            h = self.flatten(nn_ops.obs_conv(x, self.conv.weight, self.conv.bias, relu=True, rows=rows, cobs=cobs))
         else:
             h = self.flatten(self.relu(self.conv(x if rows is None else x[rows])))
         if actions is None:
+            cache = getattr(self, "_head_cache", None) if getattr(self, "_head_cache_live", False) else None
+            if cache is not None and h.dtype == torch.bfloat16 and not torch.is_grad_enabled():
+                # rollout: the 13,536-wide bf16 copy of the head's weights made once per rollout (cache_inference_weights)
+                return F.linear(h, cache[0], cache[1])[:, : self.policy_head.out_features], self.value_head(h)
             return padded_linear(h, self.policy_head), self.value_head(h)
         value = self.value_head(h).squeeze(-1)
         if h.is_cuda and h.dtype == torch.bfloat16 and legal_mask is not None:
             log_probs, entropy = nn_ops.policy_head_evaluate(h, self.policy_head, legal_mask, actions, mask_rows)
             return log_probs, entropy, value
         return self.evaluate_from_logits(padded_linear(h, self.policy_head), value, actions, legal_mask, mask_rows)
+
+
+    def cache_inference_weights(self, live: bool = True) -> None:
+        """Refresh the padded bf16 copy of the policy head that no-grad bf16 forwards use while ``live`` (a rollout: the
+        parameters do not change during it, so the per-step pad (70 MB) + autocast cast (105 MB) of ``padded_linear`` is
+        paid once per rollout); ``live=False`` switches the copy off again.  The buffers keep their addresses, so a
+        captured rollout graph reads the refreshed values."""
+        object.__setattr__(self, "_head_cache_live", bool(live))
+        if not live:
+            return
+        lin = self.policy_head
+        pad = (-lin.out_features) % 16
+        if getattr(self, "_head_cache", None) is None:
+            w = torch.zeros((lin.out_features + pad, lin.in_features), dtype=torch.bfloat16, device=lin.weight.device)
+            b = torch.zeros(lin.out_features + pad, dtype=torch.bfloat16, device=lin.weight.device)
+            object.__setattr__(self, "_head_cache", (w, b))  # plain attribute: not a parameter / buffer, not in state_dict
+        w, b = self._head_cache
+        with torch.no_grad():
+            w[: lin.out_features].copy_(lin.weight)
+            if lin.bias is not None:
+                b[: lin.out_features].copy_(lin.bias)
 
 
 class SqueezeExcitation(nn.Module):

@@ -156,6 +156,9 @@ class RolloutBuffer:
         d, T, N = self.device, self.T, self.N
         self.obs = torch.zeros((T + 1, N, 46, 9, 9), dtype=torch.float32, device=d)
         self.bitmaps = torch.zeros((T + 1, N, nv.BITMAP_WORDS), dtype=torch.int32, device=d)
+        # compact observations (160 B each: piece-plane index per square + the constant-plane values), written by the
+        # engine beside obs[t]: what the policy network's input layer reads in the rollout and in every update epoch
+        self.cobs = torch.zeros((T + 1, N, nv.COBS_WORDS), dtype=torch.int32, device=d)
         self.actions = torch.zeros((T, N), dtype=torch.int64, device=d)
         self.log_probs = torch.zeros((T, N), dtype=torch.float32, device=d)
         self.values = torch.zeros((T, N), dtype=torch.float32, device=d)
@@ -194,7 +197,8 @@ class RolloutBuffer:
                  "log_probs": self.log_probs.reshape(B), "values": self.values.reshape(B),
                  "rewards": self.rewards.reshape(B), "advantages": self.advantages.reshape(B),
                  "returns": self.returns.reshape(B), "dones": self.dones.reshape(B).bool(),
-                 "legal_bitmaps": self.bitmaps[:T].reshape(B, nv.BITMAP_WORDS)}
+                 "legal_bitmaps": self.bitmaps[:T].reshape(B, nv.BITMAP_WORDS),
+                 "compact_obs": self.cobs[:T].reshape(B, nv.COBS_WORDS)}
         if expand_masks:
             batch["legal_masks"] = self.legal_masks()
         return batch
@@ -203,4 +207,5 @@ class RolloutBuffer:
         """Start the next rollout from the last written state: slot T becomes slot 0."""
         self.obs[0].copy_(self.obs[self.T])
         self.bitmaps[0].copy_(self.bitmaps[self.T])
+        self.cobs[0].copy_(self.cobs[self.T])
         self._advantages_computed = False

@@ -105,13 +105,17 @@ class PPOAgent:
         return torch.autocast("cuda", dtype=torch.bfloat16, enabled=bool(self.use_mixed_precision and self.device.type == "cuda"))
 
     def select_actions(self, obs: torch.Tensor, legal_mask: torch.Tensor, *, is_training: bool = True,
-                       out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
-                       ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                       out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, cobs: Optional[torch.Tensor] = None,
+                       draw_counter: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """Batched select_action: obs [N,46,9,9] and legal_mask [N,13527] (or the engine's legal bitmap rows, int32
         [N,448]) stay on the device; returns (actions int64 [N], log_probs fp32 [N], values fp32 [N]) without any
         host synchronisation.  ``out`` = (actions, log_probs) rows of the rollout storage to write into."""
         self.model.train(is_training)
         kw = {"out": out} if out is not None else {}
+        if cobs is not None and not self._is_obs_scaler():
+            kw["cobs"] = cobs  # the engine's compact observations of `obs` (input layers that read them skip the 14.9 KB rows)
+        if draw_counter is not None:
+            kw["draw_counter"] = draw_counter  # device-side sampling counter (CUDA-graph rollouts)
         with torch.no_grad(), self._autocast():
             action, log_prob, value = self.model.get_action_and_value(self._scale(obs), legal_mask=legal_mask,
                                                                       deterministic=not is_training, **kw)
@@ -131,10 +135,11 @@ class PPOAgent:
             return None, -1, 0.0, v
         return move, idx, lp, v
 
-    def get_values(self, obs: torch.Tensor) -> torch.Tensor:
+    def get_values(self, obs: torch.Tensor, cobs: Optional[torch.Tensor] = None) -> torch.Tensor:
         self.model.eval()
+        use_cobs = cobs is not None and not self._is_obs_scaler() and getattr(self.model, "reads_compact_obs", False)
         with torch.no_grad(), self._autocast():
-            _, value = self.model(self._scale(obs))
+            _, value = self.model(obs, cobs=cobs) if use_cobs else self.model(self._scale(obs))
         if value.dim() > 1 and value.shape[-1] == 1:
             value = value.squeeze(-1)
         return value.float()
@@ -171,6 +176,8 @@ class PPOAgent:
         in_place = (getattr(getattr(self.model, "module", self.model), "fused_minibatch", False)
                     and not self._is_obs_scaler() and d.type == "cuda")
         S = {"obs": obs_b, "act": act_b, "oldlp": oldlp_b, "oldv": oldv_b, "adv": adv_b, "ret": ret_b, "mask": mask_b}
+        if "compact_obs" in batch and getattr(getattr(self.model, "module", self.model), "reads_compact_obs", False):
+            S["cobs"] = batch["compact_obs"].to(d)
         graphed = (in_place and self.cuda_graph_update and getattr(self, "_ddp", None) is None and self.scheduler is None
                    and n >= self.minibatch_size)
         if graphed:
@@ -205,8 +212,9 @@ class PPOAgent:
             if in_place:
                 # observations and masks are read in place from the rollout storage through the minibatch indices;
                 # input layer and policy head + masked evaluation are fused nodes (nn_ops.py)
+                extra = {"cobs": S["cobs"]} if "cobs" in S else {}
                 new_lp, entropy, new_v = self._train_forward(S["obs"], rows=mb, actions=S["act"][mb], legal_mask=S["mask"],
-                                                             mask_rows=mb)
+                                                             mask_rows=mb, **extra)
             else:
                 logits, values = self._train_forward(self._scale(S["obs"][mb]))
                 new_lp, entropy, new_v = type(self.model).evaluate_from_logits(logits, values, S["act"][mb], S["mask"],

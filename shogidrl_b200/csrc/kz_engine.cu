@@ -591,6 +591,7 @@ struct StepParams {
   int* tile_counter;  // zeroed per launch: tiles (8 games, one per warp) beyond the first are claimed dynamically
   uint32_t* bitmap_out;  // the legal bitmap [n][bitmap_stride] (modes 0-2; mode 2 writes it instead of the mask row)
   long long bitmap_stride;  // words per bitmap row (>= BITMAP_WORDS, a multiple of 4)
+  uint32_t* cobs_out;  // optional compact observation [n][KZ_COBS_WORDS] (kz_step_rollout / kz_legal_bitmap)
 };
 
 __device__ __forceinline__ uint32_t rand32(unsigned long long seed, unsigned long long env, unsigned long long step) {
@@ -1225,6 +1226,35 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
     if constexpr (MODE != 2) write_mask();
     pick_next();
     write_obs();
+    if (P.cobs_out) {
+      // compact observation: what the 46 planes are made of -- per observation square (already rotated for White to move)
+      // the index of the one piece plane that holds a 1 there (0xFF: none), and the 18 constant-plane values.  160 bytes
+      // instead of 14,904: the input layer of the policy network reads this form (kz_cobs_conv_*, csrc/kz_nn.cu).
+      __syncwarp();
+      uint8_t* cb = reinterpret_cast<uint8_t*>(ws.oimg);
+      if (lane < 21) ws.oimg[lane] = 0xFFFFFFFFu;
+      float pv = 0.f;
+      if (lane < 14) {
+        const int cnt = ws.meta[lane < 7 ? side * 7 + lane : (1 - side) * 7 + (lane - 7)];
+        if (cnt > 0) pv = __fdiv_rn((float)cnt, 18.0f);
+      } else if (lane == 14) pv = side == 0 ? 1.f : 0.f;
+      else if (lane == 15) pv = max_moves > 0 ? __fdiv_rn((float)move_count, (float)max_moves) : 0.f;
+      if (lane < 19) ws.oimg[21 + lane] = lane < 18 ? __float_as_uint(pv) : 0u;
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const int sq = lane + 32 * j;
+        const int code = sq < 81 ? ws.board[sq] : 0;
+        if (code) {
+          const int t = code_type(code), mine = code_color(code) == side;
+          cb[side == 0 ? sq : 80 - sq] = (uint8_t)(t < 8 ? (mine ? 0 : 14) + t : (mine ? 8 : 22) + (t - 8));
+        }
+      }
+      __syncwarp();
+      uint32_t* dst = P.cobs_out + (size_t)g * KZ_COBS_WORDS;
+      for (int i = lane; i < KZ_COBS_WORDS; i += 32) dst[i] = ws.oimg[i];
+      __syncwarp();
+    }
 
     // ---- store state
     __syncwarp();
@@ -1571,6 +1601,7 @@ int launch_step(void* state, int n, int hist_cap, StepParams P, cudaStream_t st,
   if (P.bitmap_out) {
     if (((uintptr_t)P.bitmap_out & 15) || P.bitmap_stride < BITMAP_WORDS || (P.bitmap_stride & 3)) return KZ_E_ARG;
   } else if (P.mode == 2) return KZ_E_ARG;
+  if (P.cobs_out && ((uintptr_t)P.cobs_out & 3)) return KZ_E_ARG;
   P.mask_vec = 0;
   if (P.mask) {
     if (P.mask_stride < KZ_NUM_ACTIONS) return KZ_E_ARG;
@@ -1803,14 +1834,14 @@ int kz_step(void* state, int n, int hist_cap, const void* actions, int actions_i
 
 int kz_step_range(void* state, int n, int hist_cap, int first, int count, int counter_slot, const void* actions,
                   int actions_i64, float* obs, int64_t obs_stride, uint8_t* mask, int64_t mask_stride, uint32_t* bitmap,
-                  int64_t bitmap_stride_words, float* reward, uint8_t* done, uint8_t* reason, int8_t* winner, int32_t* ep_len,
-                  int32_t* legal_count, void* next_actions, uint64_t seed, uint32_t rng_step, uint32_t env_offset,
-                  int auto_reset, void* stream) {
+                  int64_t bitmap_stride_words, uint32_t* cobs, float* reward, uint8_t* done, uint8_t* reason, int8_t* winner,
+                  int32_t* ep_len, int32_t* legal_count, void* next_actions, uint64_t seed, uint32_t rng_step,
+                  uint32_t env_offset, int auto_reset, void* stream) {
   if (!actions || (mask && bitmap)) return KZ_E_ARG;
   StepParams P{};
   P.actions = actions; P.actions_i64 = actions_i64;
   P.obs = obs; P.obs_stride = obs_stride; P.mask = mask; P.mask_stride = mask_stride;
-  P.bitmap_out = bitmap; P.bitmap_stride = bitmap_stride_words;
+  P.bitmap_out = bitmap; P.bitmap_stride = bitmap_stride_words; P.cobs_out = cobs;
   P.reward = reward; P.done = done; P.reason = reason; P.winner = winner; P.ep_len = ep_len;
   P.legal_count = legal_count; P.next_actions = next_actions;
   P.seed = seed; P.rng_step = rng_step; P.env_offset = env_offset;
@@ -1855,14 +1886,14 @@ int kz_expand(const void* state, int n, int hist_cap, const uint32_t* bitmap, fl
 }
 
 int kz_step_rollout(void* state, int n, int hist_cap, const void* actions, int actions_i64, float* obs, int64_t obs_stride,
-                    uint32_t* bitmap, int64_t bitmap_stride_words, float* reward, uint8_t* done, uint8_t* reason,
+                    uint32_t* bitmap, int64_t bitmap_stride_words, uint32_t* cobs, float* reward, uint8_t* done, uint8_t* reason,
                     int8_t* winner, int32_t* ep_len, int32_t* legal_count, void* next_actions, uint64_t seed,
                     uint32_t rng_step, uint32_t env_offset, int auto_reset, void* stream) {
   if (!actions || !bitmap) return KZ_E_ARG;
   StepParams P{};
   P.actions = actions; P.actions_i64 = actions_i64;
   P.obs = obs; P.obs_stride = obs_stride;
-  P.bitmap_out = bitmap; P.bitmap_stride = bitmap_stride_words;
+  P.bitmap_out = bitmap; P.bitmap_stride = bitmap_stride_words; P.cobs_out = cobs;
   P.reward = reward; P.done = done; P.reason = reason; P.winner = winner; P.ep_len = ep_len;
   P.legal_count = legal_count; P.next_actions = next_actions;
   P.seed = seed; P.rng_step = rng_step; P.env_offset = env_offset;
@@ -1871,11 +1902,11 @@ int kz_step_rollout(void* state, int n, int hist_cap, const void* actions, int a
 }
 
 int kz_legal_bitmap(void* state, int n, int hist_cap, float* obs, int64_t obs_stride, uint32_t* bitmap,
-                    int64_t bitmap_stride_words, int32_t* legal_count, void* stream) {
+                    int64_t bitmap_stride_words, uint32_t* cobs, int32_t* legal_count, void* stream) {
   if (!bitmap) return KZ_E_ARG;
   StepParams P{};
   P.obs = obs; P.obs_stride = obs_stride;
-  P.bitmap_out = bitmap; P.bitmap_stride = bitmap_stride_words;
+  P.bitmap_out = bitmap; P.bitmap_stride = bitmap_stride_words; P.cobs_out = cobs;
   P.legal_count = legal_count;
   P.mode = 0;
   return launch_step(state, n, hist_cap, P, reinterpret_cast<cudaStream_t>(stream));

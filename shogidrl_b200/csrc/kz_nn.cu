@@ -173,12 +173,18 @@ __global__ void __launch_bounds__(128) kz_obs_conv_fwd_kernel(const float* __res
 }
 
 // ---- weight gradient: 9 warps, warp t owns tap t: dW[o][t][c] += sum_xy dy[o][xy] * tile[row(xy) + off(t)][c] ----
+// COBS: the board comes as the engine's compact observation (kz_step_rollout: 160 bytes -- one piece-plane index per
+// square + the 18 constant-plane values) instead of the 14,904-byte fp32 tensor: the tile is then PATCHED from one board
+// to the next (clear the previous board's piece channel of each square, set the new one, rewrite the constant channels)
+// instead of being converted from 3,726 floats, and the kernel stops being bound by those loads.
+template <bool COBS>
 __global__ void __launch_bounds__(288) kz_obs_conv_wgrad_kernel(const float* __restrict__ obs,
                                                                 const long long* __restrict__ rows,
                                                                 const __nv_bfloat16* __restrict__ y, const void* dout,
                                                                 int dout_bf16, int n, float* __restrict__ part) {
   __shared__ __align__(16) __nv_bfloat16 xs[XS_ROWS * XS_STRIDE];
   __shared__ __align__(16) __nv_bfloat16 ds[COUT * DS_STRIDE];
+  __shared__ __align__(16) uint32_t cws[KZ_COBS_WORDS];
   const int tid = threadIdx.x, lane = tid & 31, tap = tid >> 5;
   init_tile(xs, tid, 288);
   for (int i = tid; i < COUT * DS_STRIDE; i += 288) ds[i] = __float2bfloat16(0.f);
@@ -205,13 +211,23 @@ __global__ void __launch_bounds__(288) kz_obs_conv_wgrad_kernel(const float* __r
     }
   };
   auto board = [&](int b) { return obs + (size_t)(rows ? rows[b] : b) * CIN * 81; };
+  uint32_t cw = 0;      // COBS: this thread's word of the next board's compact observation
+  int prev_plane = 0xFF;  // COBS: the piece channel this thread's square holds in the tile
+  auto load_cobs = [&](int b) {
+    if (tid < KZ_COBS_WORDS) cw = __ldg(reinterpret_cast<const uint32_t*>(obs) + (size_t)(rows ? rows[b] : b) * KZ_COBS_WORDS + tid);
+  };
   if (blockIdx.x < n) {
-    load_board<288>(regs, board(blockIdx.x), tid);
+    if (COBS) load_cobs(blockIdx.x);
+    else load_board<288>(regs, board(blockIdx.x), tid);
     load_dy(blockIdx.x);
   }
   for (int b = blockIdx.x; b < n; b += gridDim.x) {
     __syncthreads();  // previous board consumed
-    store_board<288>(xs, regs, tid);
+    if (COBS) {
+      if (tid < KZ_COBS_WORDS) cws[tid] = cw;
+    } else {
+      store_board<288>(xs, regs, tid);
+    }
 #pragma unroll
     for (int k = 0; k < DSLOTS; k++) {
       const int i = tid + k * 288;
@@ -221,8 +237,26 @@ __global__ void __launch_bounds__(288) kz_obs_conv_wgrad_kernel(const float* __r
       }
     }
     __syncthreads();
+    if (COBS) {
+      if (tid < 81) {  // this square's piece channel: clear the old one, set the new one
+        const int np = reinterpret_cast<const uint8_t*>(cws)[tid];
+        __nv_bfloat16* row = xs + tile_row(tid) * XS_STRIDE;
+        if (prev_plane != np) {
+          if (prev_plane < 28) row[prev_plane] = __float2bfloat16(0.f);
+          if (np < 28) row[np] = __float2bfloat16(1.f);
+          prev_plane = np;
+        }
+      }
+      for (int i = tid; i < 81 * 9; i += 288) {  // constant channels 28..45 = tile words 14..22 of every square
+        const int sq = i / 9, k = i - sq * 9;
+        const __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(cws[21 + 2 * k]), __uint_as_float(cws[22 + 2 * k]));
+        reinterpret_cast<__nv_bfloat162*>(xs + tile_row(sq) * XS_STRIDE)[14 + k] = v;
+      }
+      __syncthreads();
+    }
     if (b + gridDim.x < n) {  // next board in flight during the products
-      load_board<288>(regs, board(b + gridDim.x), tid);
+      if (COBS) load_cobs(b + gridDim.x);
+      else load_board<288>(regs, board(b + gridDim.x), tid);
       load_dy(b + gridDim.x);
     }
 #pragma unroll
@@ -250,6 +284,99 @@ __global__ void __launch_bounds__(288) kz_obs_conv_wgrad_kernel(const float* __r
       const int o = (lane >> 2) + (e >> 1) * 8, c = j * 8 + (lane & 3) * 2 + (e & 1);
       p[(o * 9 + tap) * CPAD + c] = acc[j][e];
     }
+}
+
+// ---- forward from the compact observation: no dense product at all.  A square holds at most one piece, so among
+// the 28 piece planes at most one input is non-zero per (output square, tap): out[o][xy] = b[o] + sum over the 9 taps of
+// W[o][plane_of(xy + tap)][tap] where that neighbour is occupied, + sum over the non-zero constant planes of
+// value x (sum of that plane's weights over the taps that fall on the board at xy: 9 position classes).  ~12 k additions
+// per board instead of 536 k multiply-adds and 160 bytes read instead of 14,904.  Operands are rounded to bf16 and
+// accumulated in fp32 like the tensor-core path (same products; the constant planes' tap sums are formed first).
+constexpr int WP_STRIDE = 9 * COUT + 4;  // floats per plane: rows of different planes fall into different bank groups
+__global__ void __launch_bounds__(128) kz_cobs_conv_fwd_kernel(const uint32_t* __restrict__ cobs,
+                                                               const long long* __restrict__ rows,
+                                                               const float* __restrict__ w, const float* __restrict__ bias,
+                                                               int n, int relu, __nv_bfloat16* __restrict__ out) {
+  __shared__ __align__(16) float Wp[28 * WP_STRIDE];       // [plane][tap][o]
+  __shared__ __align__(16) float Rc[18 * 9 * COUT];        // [constant plane][position class][o]
+  __shared__ __align__(16) float Bc[COUT];
+  __shared__ __align__(16) uint32_t cbs[4][KZ_COBS_WORDS];
+  __shared__ __align__(16) __nv_bfloat16 ys[4][COUT * 81 + 8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto r16 = [](float v) { return __bfloat162float(__float2bfloat16(v)); };
+  for (int i = tid; i < 28 * 9 * COUT; i += 128) {
+    const int p = i / (9 * COUT), r = i - p * 9 * COUT, tap = r / COUT, o = r - tap * COUT;
+    Wp[p * WP_STRIDE + tap * COUT + o] = r16(w[(o * CIN + p) * 9 + tap]);
+  }
+  for (int i = tid; i < 18 * 9 * COUT; i += 128) {
+    const int c = i / (9 * COUT), r = i - c * 9 * COUT, cls = r / COUT, o = r - cls * COUT;
+    const int rc = cls / 3, cc = cls - rc * 3;  // 0: first row / column, 1: inner, 2: last
+    float sum = 0.f;
+    for (int tap = 0; tap < 9; tap++) {
+      const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+      if ((rc == 0 && dy < 0) || (rc == 2 && dy > 0) || (cc == 0 && dx < 0) || (cc == 2 && dx > 0)) continue;
+      sum += r16(w[(o * CIN + 28 + c) * 9 + tap]);
+    }
+    Rc[i] = sum;
+  }
+  if (tid < COUT) Bc[tid] = bias ? r16(bias[tid]) : 0.f;
+  __syncthreads();
+  const uint8_t* sqp = reinterpret_cast<const uint8_t*>(cbs[warp]);
+  for (int b = blockIdx.x * 4 + warp; b < n; b += gridDim.x * 4) {
+    const uint32_t* src = cobs + (size_t)(rows ? rows[b] : b) * KZ_COBS_WORDS;
+    __syncwarp();
+    cbs[warp][lane] = __ldg(src + lane);
+    if (lane < KZ_COBS_WORDS - 32) cbs[warp][32 + lane] = __ldg(src + 32 + lane);
+    __syncwarp();
+    const float pv = lane < 18 ? r16(__uint_as_float(cbs[warp][21 + lane])) : 0.f;
+    const uint32_t nz = __ballot_sync(0xffffffffu, pv != 0.f);
+#pragma unroll 1
+    for (int j = 0; j < 3; j++) {
+      const int xy = lane + 32 * j;
+      const bool act = xy < 81;
+      const int r = act ? xy / 9 : 0, c = act ? xy - 9 * r : 0;
+      float acc[COUT];
+#pragma unroll
+      for (int o = 0; o < COUT; o++) acc[o] = Bc[o];
+      if (act) {
+#pragma unroll
+        for (int tap = 0; tap < 9; tap++) {
+          const int rr = r + tap / 3 - 1, cc = c + tap % 3 - 1;
+          if (rr < 0 || rr > 8 || cc < 0 || cc > 8) continue;
+          const int p = sqp[rr * 9 + cc];
+          if (p < 28) {
+            const float4* wv = reinterpret_cast<const float4*>(Wp + p * WP_STRIDE + tap * COUT);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const float4 t = wv[q];
+              acc[4 * q] += t.x; acc[4 * q + 1] += t.y; acc[4 * q + 2] += t.z; acc[4 * q + 3] += t.w;
+            }
+          }
+        }
+      }
+      const int cls = (r == 0 ? 0 : (r == 8 ? 2 : 1)) * 3 + (c == 0 ? 0 : (c == 8 ? 2 : 1));
+      uint32_t m = nz;
+      while (m) {  // warp-uniform
+        const int i = __ffs(m) - 1;
+        m &= m - 1;
+        const float v = __shfl_sync(0xffffffffu, pv, i);
+        const float4* rv = reinterpret_cast<const float4*>(Rc + (i * 9 + cls) * COUT);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const float4 t = rv[q];
+          acc[4 * q] = fmaf(v, t.x, acc[4 * q]); acc[4 * q + 1] = fmaf(v, t.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(v, t.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(v, t.w, acc[4 * q + 3]);
+        }
+      }
+      if (act) {
+#pragma unroll
+        for (int o = 0; o < COUT; o++) ys[warp][o * 81 + xy] = __float2bfloat16(relu ? fmaxf(acc[o], 0.f) : acc[o]);
+      }
+    }
+    __syncwarp();
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)b * COUT * 81);  // 2,592 B per board: 16-byte aligned
+    for (int i = lane; i < COUT * 81 * 2 / 16; i += 32) dst[i] = reinterpret_cast<const uint4*>(ys[warp])[i];
+  }
 }
 
 // sum the per-CTA partials; scatter into the [16][46][3][3] weight layout and the bias gradient
@@ -291,15 +418,45 @@ int kz_obs_conv_fwd(const float* obs, const int64_t* obs_rows, const float* weig
 }
 
 int kz_obs_conv_wgrad_ctas(int n) {
-  static const int resident = resident_ctas(kz_obs_conv_wgrad_kernel, 288);
+  static const int resident = resident_ctas(kz_obs_conv_wgrad_kernel<false>, 288);
   return n < resident ? (n > 0 ? n : 1) : resident;
+}
+
+int kz_cobs_conv_wgrad_ctas(int n) {
+  static const int resident = resident_ctas(kz_obs_conv_wgrad_kernel<true>, 288);
+  return n < resident ? (n > 0 ? n : 1) : resident;
+}
+
+int kz_cobs_conv_fwd(const uint32_t* cobs, const int64_t* cobs_rows, const float* weight, const float* bias, int cout, int n,
+                     int relu, void* out_bf16, void* stream) {
+  if (!cobs || !weight || !out_bf16 || n <= 0 || cout != COUT || ((uintptr_t)cobs & 3)) return KZ_E_ARG;
+  static const int resident = resident_ctas(kz_cobs_conv_fwd_kernel, 128);
+  const int want = (n + 3) / 4;
+  kz_cobs_conv_fwd_kernel<<<want < resident ? want : resident, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      cobs, reinterpret_cast<const long long*>(cobs_rows), weight, bias, n, relu, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? KZ_OK : fail(e);
+}
+
+int kz_cobs_conv_wgrad(const uint32_t* cobs, const int64_t* cobs_rows, const void* y_bf16, const void* dout, int dout_bf16,
+                       int cout, int n, float* workspace, int ctas, float* dweight, float* dbias, void* stream) {
+  if (!cobs || !dout || !workspace || !dweight || n <= 0 || cout != COUT || ctas <= 0 || ctas > n || ((uintptr_t)cobs & 3))
+    return KZ_E_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  kz_obs_conv_wgrad_kernel<true><<<ctas, 288, 0, st>>>(reinterpret_cast<const float*>(cobs),
+                                                       reinterpret_cast<const long long*>(cobs_rows),
+                                                       reinterpret_cast<const __nv_bfloat16*>(y_bf16), dout, dout_bf16, n,
+                                                       workspace);
+  kz_obs_conv_wgrad_reduce_kernel<<<(COUT * KTOT + 127) / 128, 128, 0, st>>>(workspace, ctas, dweight, dbias);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? KZ_OK : fail(e);
 }
 
 int kz_obs_conv_wgrad(const float* obs, const int64_t* obs_rows, const void* y_bf16, const void* dout, int dout_bf16,
                       int cout, int n, float* workspace, int ctas, float* dweight, float* dbias, void* stream) {
   if (!obs || !dout || !workspace || !dweight || n <= 0 || cout != COUT || ctas <= 0 || ctas > n) return KZ_E_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  kz_obs_conv_wgrad_kernel<<<ctas, 288, 0, st>>>(obs, reinterpret_cast<const long long*>(obs_rows),
+  kz_obs_conv_wgrad_kernel<false><<<ctas, 288, 0, st>>>(obs, reinterpret_cast<const long long*>(obs_rows),
                                                  reinterpret_cast<const __nv_bfloat16*>(y_bf16), dout, dout_bf16, n, workspace);
   kz_obs_conv_wgrad_reduce_kernel<<<(COUT * KTOT + 127) / 128, 128, 0, st>>>(workspace, ctas, dweight, dbias);
   cudaError_t e = cudaGetLastError();

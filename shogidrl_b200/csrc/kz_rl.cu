@@ -160,11 +160,13 @@ __device__ __forceinline__ void each_legal_of_row(const WIN& W, int lane, LegalL
 template <class WIN>  // MaskWindows: byte mask rows; BitmapWindows: 448-word legal bitmap rows.  ldm in bytes.
 __global__ void __launch_bounds__(256, 4) kz_sample_kernel(const void* logits, int bf16, long long ld, const void* mask,
                                                         long long ldm, int n, unsigned long long seed,
-                                                        unsigned long long offset, void* actions, int actions_i64,
-                                                        float* logp, float* entropy, int deterministic) {
+                                                        unsigned long long offset, const unsigned long long* offset_dev,
+                                                        void* actions, int actions_i64, float* logp, float* entropy,
+                                                        int deterministic) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
+  if (offset_dev) offset += *offset_dev;  // draw counter kept on the device: a captured launch draws fresh numbers on replay
   const char* lrow = reinterpret_cast<const char*>(logits) + (size_t)row * ld * (bf16 ? 2 : 4);
   const WIN W(reinterpret_cast<const char*>(mask) + (size_t)row * ldm);
   __shared__ uint16_t s_list[8][LIST_CAP];
@@ -507,35 +509,37 @@ __global__ void __launch_bounds__(1024) kz_ppo_loss_kernel(const float* __restri
 extern "C" {
 
 static int sample_impl(const void* logits, int logits_bf16, int64_t ld, const void* mask, int64_t ldm_bytes, int bitmap, int n,
-                       uint64_t seed, uint64_t offset, void* actions, int actions_i64, float* logp, float* entropy,
-                       int deterministic, void* stream) {
+                       uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* actions, int actions_i64, float* logp,
+                       float* entropy, int deterministic, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned long long* od = reinterpret_cast<const unsigned long long*>(offset_dev);
   if (bitmap)
-    kz_sample_kernel<BitmapWindows><<<(n + 7) / 8, 256, 0, st>>>(logits, logits_bf16, ld, mask, ldm_bytes, n, seed, offset,
+    kz_sample_kernel<BitmapWindows><<<(n + 7) / 8, 256, 0, st>>>(logits, logits_bf16, ld, mask, ldm_bytes, n, seed, offset, od,
                                                                   actions, actions_i64, logp, entropy, deterministic);
   else
-    kz_sample_kernel<MaskWindows><<<(n + 7) / 8, 256, 0, st>>>(logits, logits_bf16, ld, mask, ldm_bytes, n, seed, offset,
+    kz_sample_kernel<MaskWindows><<<(n + 7) / 8, 256, 0, st>>>(logits, logits_bf16, ld, mask, ldm_bytes, n, seed, offset, od,
                                                                 actions, actions_i64, logp, entropy, deterministic);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? KZ_OK : fail(e);
 }
 
 int kz_sample_masked(const void* logits, int logits_bf16, int64_t ld, const uint8_t* mask, int64_t ldm, int n,
-                     uint64_t seed, uint64_t offset, void* actions, int actions_i64, float* logp, float* entropy,
-                     int deterministic, void* stream) {
-  if (!logits || !mask || !actions || n <= 0 || ld < KZ_NUM_ACTIONS || ldm < KZ_NUM_ACTIONS) return KZ_E_ARG;
-  return sample_impl(logits, logits_bf16, ld, mask, ldm, 0, n, seed, offset, actions, actions_i64, logp, entropy,
+                     uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* actions, int actions_i64, float* logp,
+                     float* entropy, int deterministic, void* stream) {
+  if (!logits || !mask || !actions || n <= 0 || ld < KZ_NUM_ACTIONS || ldm < KZ_NUM_ACTIONS || ((uintptr_t)offset_dev & 7))
+    return KZ_E_ARG;
+  return sample_impl(logits, logits_bf16, ld, mask, ldm, 0, n, seed, offset, offset_dev, actions, actions_i64, logp, entropy,
                      deterministic, stream);
 }
 
 int kz_sample_bitmap(const void* logits, int logits_bf16, int64_t ld, const uint32_t* bitmap, int64_t ldb_words, int n,
-                     uint64_t seed, uint64_t offset, void* actions, int actions_i64, float* logp, float* entropy,
-                     int deterministic, void* stream) {
+                     uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* actions, int actions_i64, float* logp,
+                     float* entropy, int deterministic, void* stream) {
   if (!logits || !bitmap || !actions || n <= 0 || ld < KZ_NUM_ACTIONS || ldb_words < KZ_BITMAP_WORDS_MIN ||
-      ((uintptr_t)bitmap & 3))
+      ((uintptr_t)bitmap & 3) || ((uintptr_t)offset_dev & 7))
     return KZ_E_ARG;
-  return sample_impl(logits, logits_bf16, ld, bitmap, ldb_words * 4, 1, n, seed, offset, actions, actions_i64, logp, entropy,
-                     deterministic, stream);
+  return sample_impl(logits, logits_bf16, ld, bitmap, ldb_words * 4, 1, n, seed, offset, offset_dev, actions, actions_i64, logp,
+                     entropy, deterministic, stream);
 }
 
 int kz_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_value, int T, int N,

@@ -29,7 +29,7 @@ def _is_bitmap(mask: torch.Tensor) -> bool:
 
 class _ObsConv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, obs, weight, bias, relu, rows):
+    def forward(ctx, obs, weight, bias, relu, rows, cobs):
         dev = nv.require_cuda(obs.device)
         nv.require(obs.dtype == torch.float32 and obs.dim() == 4 and tuple(obs.shape[1:]) == (46, 9, 9), "obs.dtype == torch.float32 and obs.dim() == 4 and tuple(obs.shape[1:]) == (46, 9, 9)")
         nv.require(tuple(weight.shape) == (16, 46, 3, 3), "tuple(weight.shape) == (16, 46, 3, 3)")
@@ -40,16 +40,24 @@ class _ObsConv(torch.autograd.Function):
         w = weight.detach().float().contiguous()
         b = bias.detach().float().contiguous() if bias is not None else None
         y = torch.empty((n, 16, 9, 9), dtype=torch.bfloat16, device=dev)
-        nv.check(nv.lib().kz_obs_conv_fwd(obs.data_ptr(), nv.ptr(rows), w.data_ptr(), nv.ptr(b), 16, n, int(relu),
-                                          y.data_ptr(), nv.stream_ptr(dev)), "kz_obs_conv_fwd")
-        ctx.save_for_backward(obs, y, rows)
+        if cobs is not None:
+            # the engine's compact observations of the same positions: 160 bytes per board instead of 14,904
+            nv.require(cobs.dtype == torch.int32 and cobs.dim() == 2 and cobs.shape[1] == nv.COBS_WORDS and cobs.is_contiguous()
+                       and cobs.device == dev and cobs.shape[0] == obs.shape[0],
+                       "cobs: contiguous int32 [len(obs), 40] compact observations on the observations' device")
+            nv.check(nv.lib().kz_cobs_conv_fwd(cobs.data_ptr(), nv.ptr(rows), w.data_ptr(), nv.ptr(b), 16, n, int(relu),
+                                               y.data_ptr(), nv.stream_ptr(dev)), "kz_cobs_conv_fwd")
+        else:
+            nv.check(nv.lib().kz_obs_conv_fwd(obs.data_ptr(), nv.ptr(rows), w.data_ptr(), nv.ptr(b), 16, n, int(relu),
+                                              y.data_ptr(), nv.stream_ptr(dev)), "kz_obs_conv_fwd")
+        ctx.save_for_backward(obs, y, rows, cobs)
         ctx.relu, ctx.has_bias = bool(relu), bias is not None
         ctx.wdtype = weight.dtype
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        obs, y, rows = ctx.saved_tensors
+        obs, y, rows, cobs = ctx.saved_tensors
         assert not ctx.needs_input_grad[0], "observations are data: the input layer has no input gradient"
         dev = obs.device
         n = y.shape[0]
@@ -57,20 +65,25 @@ class _ObsConv(torch.autograd.Function):
             dy = dy.float()
         dy = dy.contiguous()
         L = nv.lib()
-        ctas = L.kz_obs_conv_wgrad_ctas(n)
+        ctas = L.kz_cobs_conv_wgrad_ctas(n) if cobs is not None else L.kz_obs_conv_wgrad_ctas(n)
         ws = torch.empty(ctas * 16 * 432, dtype=torch.float32, device=dev)
         dw = torch.empty((16, 46, 3, 3), dtype=torch.float32, device=dev)
         db = torch.empty(16, dtype=torch.float32, device=dev) if ctx.has_bias else None
-        nv.check(L.kz_obs_conv_wgrad(obs.data_ptr(), nv.ptr(rows), y.data_ptr() if ctx.relu else None, dy.data_ptr(),
-                                     int(dy.dtype == torch.bfloat16), 16, n, ws.data_ptr(), ctas, dw.data_ptr(), nv.ptr(db),
-                                     nv.stream_ptr(dev)), "kz_obs_conv_wgrad")
-        return None, dw.to(ctx.wdtype), (db.to(ctx.wdtype) if db is not None else None), None, None
+        args = (nv.ptr(rows), y.data_ptr() if ctx.relu else None, dy.data_ptr(), int(dy.dtype == torch.bfloat16), 16, n,
+                ws.data_ptr(), ctas, dw.data_ptr(), nv.ptr(db), nv.stream_ptr(dev))
+        if cobs is not None:
+            nv.check(L.kz_cobs_conv_wgrad(cobs.data_ptr(), *args), "kz_cobs_conv_wgrad")
+        else:
+            nv.check(L.kz_obs_conv_wgrad(obs.data_ptr(), *args), "kz_obs_conv_wgrad")
+        return None, dw.to(ctx.wdtype), (db.to(ctx.wdtype) if db is not None else None), None, None, None
 
 
 def obs_conv(obs: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = True,
-             rows: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """bf16 [n, 16, 9, 9] = [relu](conv3x3(obs[rows], weight) + bias), operands rounded to bf16, fp32 accumulation."""
-    return _ObsConv.apply(obs, weight, bias, relu, rows)
+             rows: Optional[torch.Tensor] = None, cobs: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bf16 [n, 16, 9, 9] = [relu](conv3x3(obs[rows], weight) + bias), operands rounded to bf16, fp32 accumulation.
+    ``cobs`` (int32 [len(obs), 40]): the engine's compact observations of the same positions (kz_step_rollout); the layer
+    then reads those 160 bytes per board instead of the 14,904-byte tensor rows -- same function of the same positions."""
+    return _ObsConv.apply(obs, weight, bias, relu, rows, cobs)
 
 
 def obs_conv_applicable(conv: torch.nn.Conv2d, x: torch.Tensor) -> bool:
@@ -106,6 +119,7 @@ class _PolicyHeadEval(torch.autograd.Function):
                      nv.stream_ptr(dev)), "kz_eval_masked_fwd")
         ctx.save_for_backward(hb, wp, logits, mask, mask_rows, actions, saved)
         ctx.has_bias, ctx.hdtype, ctx.wdtype = bias is not None, h.dtype, weight.dtype
+        ctx.weight_param = weight if isinstance(weight, torch.nn.Parameter) else None
         return logp, ent
 
     @staticmethod
@@ -130,9 +144,13 @@ class _PolicyHeadEval(torch.autograd.Function):
             nv.check(nv.lib().kz_eval_masked_bwd(*common, nv.stream_ptr(dev)), "kz_eval_masked_bwd")
         # the weight gradient first: under data parallelism its all-reduce (the bulk of the model's gradient bytes) starts
         # here and overlaps the input-gradient GEMM and everything backward still has to do (distributed.GradReducer)
-        dw = torch.mm(dlogits.t(), hb)[: nv.NUM_ACTIONS].to(ctx.wdtype) if ctx.needs_input_grad[1] else None
-        if dw is not None and grad_reducer is not None:
-            dw = grad_reducer.early(dw)
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw16 = torch.mm(dlogits.t(), hb)[: nv.NUM_ACTIONS]  # bf16, contiguous (leading rows of the padded product)
+            if grad_reducer is not None and ctx.weight_param is not None and ctx.weight_param.grad is None:
+                grad_reducer.early(ctx.weight_param, dw16)  # sets weight.grad itself once the cross-rank sum has arrived
+            else:
+                dw = dw16.to(ctx.wdtype)
         dh = torch.mm(dlogits, wp).to(ctx.hdtype) if ctx.needs_input_grad[0] else None
         db = (dbq[: nv.NUM_ACTIONS].to(torch.float64) * 2.0 ** -44).to(ctx.wdtype) if want_db else None
         return dh, dw, db, None, None, None

@@ -28,14 +28,16 @@ def _check_legal_rows(mask: torch.Tensor, what: str) -> None:
 
 def sample_masked(logits: torch.Tensor, mask: torch.Tensor, seed: int = 0, offset: int = 0,
                   deterministic: bool = False, want_entropy: bool = False,
-                  out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+                  out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, offset_tensor: Optional[torch.Tensor] = None
                   ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
     """Masked softmax -> Categorical sample (argmax if deterministic) -> log_prob, one warp per row.
 
     Mirrors BaseActorCriticModel.get_action_and_value after forward() (base_actor_critic.py:64-116):
     illegal logits -> -inf, softmax, NaN rows -> uniform, Categorical(probs) with its eps clamp.  ``mask`` is the
     byte mask [n, 13527] or the engine's legal bitmap [n, 448] int32 (kz_sample_bitmap: identical results, 7.5x fewer
-    mask bytes).  ``out`` = (actions int64 [n], log_probs fp32 [n]) writes straight into rollout storage."""
+    mask bytes).  ``out`` = (actions int64 [n], log_probs fp32 [n]) writes straight into rollout storage.
+    ``offset_tensor`` (int64 [1] on the device) is added to ``offset`` by the kernel when it runs: a draw counter that a
+    CUDA-graph replay can advance."""
     dev = nv.require_cuda(logits.device)
     nv.require(logits.dim() == 2 and logits.shape[1] == nv.NUM_ACTIONS and logits.stride(1) == 1, "logits.dim() == 2 and logits.shape[1] == nv.NUM_ACTIONS and logits.stride(1) == 1")
     nv.require(logits.dtype in (torch.float32, torch.bfloat16), "logits.dtype in (torch.float32, torch.bfloat16)")
@@ -51,9 +53,12 @@ def sample_masked(logits: torch.Tensor, mask: torch.Tensor, seed: int = 0, offse
         actions = torch.empty(n, dtype=torch.int64, device=dev)
         logp = torch.empty(n, dtype=torch.float32, device=dev)
     ent = torch.empty(n, dtype=torch.float32, device=dev) if want_entropy else None
+    if offset_tensor is not None:
+        nv.require(offset_tensor.dtype == torch.int64 and offset_tensor.numel() >= 1 and offset_tensor.device == dev,
+                   "offset_tensor: int64 [1] on the logits' device")
     fn = nv.lib().kz_sample_bitmap if is_bitmap(mask) else nv.lib().kz_sample_masked
     nv.check(fn(logits.data_ptr(), int(logits.dtype == torch.bfloat16), logits.stride(0),
-                mask.data_ptr(), mask.stride(0), n, int(seed), int(offset), actions.data_ptr(), 1,
+                mask.data_ptr(), mask.stride(0), n, int(seed), int(offset), nv.ptr(offset_tensor), actions.data_ptr(), 1,
                 logp.data_ptr(), nv.ptr(ent), int(deterministic), nv.stream_ptr(dev)),
              "kz_sample_masked")
     return actions, logp, ent

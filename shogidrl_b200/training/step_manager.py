@@ -224,24 +224,57 @@ class VecStepManager:
         self.black_wins = self.white_wins = self.draws = 0
         self._started = False
         self._stat = torch.zeros(4, dtype=torch.int64, device=env.device)
+        self._draws = torch.zeros(1, dtype=torch.int64, device=env.device)  # sampling counter, advanced on the device
+        tr = getattr(getattr(agent, "config", None), "training", None)
+        self.graph_rollout = bool(getattr(tr, "cuda_graph_rollout", True))
+        self._graph = None
+        self._eager_runs = 0
 
     def start(self) -> None:
         self.env.reset(refresh=False)
-        self.env.legal_bitmap(self.buffer.bitmaps[0], obs=self.buffer.obs[0])
+        self.env.legal_bitmap(self.buffer.bitmaps[0], obs=self.buffer.obs[0], cobs=self.buffer.cobs[0])
         self._started = True
 
     def collect(self) -> None:
         """Fill the buffer with T steps of N games.  No host synchronisation inside the loop; the sampler writes the
         action / log-prob rows and the engine writes reward / done / next observation / next legal bitmap straight
-        into the rollout storage."""
+        into the rollout storage.
+
+        The loop is launch-bound on the host side (about 25 small launches per step against ~0.8 ms of device work, and
+        worse when several ranks share the host's cores), so from the second call on the whole T-step rollout is ONE
+        CUDA graph: every address it touches is fixed (rollout storage, engine state, model parameters), the sampler's
+        draw counter lives on the device, and nothing in the loop reads device results on the host."""
         if not self._started:
             self.start()
+        model = getattr(self.agent, "model", None)
+        cached = hasattr(model, "cache_inference_weights") and getattr(self.agent, "use_mixed_precision", False)
+        if cached:
+            model.cache_inference_weights()  # once per rollout, outside the captured loop (fixed addresses)
+        try:
+            if self.graph_rollout and self.env.device.type == "cuda":
+                if self._graph is None and self._eager_runs >= 1:
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        self._collect_steps()
+                    self._graph = graph
+                if self._graph is not None:
+                    self._graph.replay()
+                    return
+            self._collect_steps()
+            self._eager_runs += 1
+        finally:
+            if cached:
+                model.cache_inference_weights(live=False)  # the parameters are about to change (PPO update)
+
+    def _collect_steps(self) -> None:
         b, env = self.buffer, self.env
         for t in range(b.T):
             _, _, value = self.agent.select_actions(b.obs[t], b.bitmaps[t], is_training=True,
-                                                    out=(b.actions[t], b.log_probs[t]))
+                                                    out=(b.actions[t], b.log_probs[t]), cobs=b.cobs[t],
+                                                    draw_counter=self._draws)
             b.values[t].copy_(value)
-            out = env.step_rollout(b.actions[t], b.obs[t + 1], b.bitmaps[t + 1], reward=b.rewards[t], done=b.dones[t])
+            out = env.step_rollout(b.actions[t], b.obs[t + 1], b.bitmaps[t + 1], reward=b.rewards[t], done=b.dones[t],
+                                   cobs=b.cobs[t + 1])
             w = out["winner"]
             d = b.dones[t] != 0
             self._stat += torch.stack([d.sum(), (d & (w == 0)).sum(), (d & (w == 1)).sum(), (d & (w < 0)).sum()])
@@ -249,7 +282,7 @@ class VecStepManager:
     def finish(self) -> Dict[str, int]:
         """Bootstrap values for the last observations, GAE; returns episode statistics (one host sync)."""
         b = self.buffer
-        last_values = self.agent.get_values(b.obs[b.T])
+        last_values = self.agent.get_values(b.obs[b.T], cobs=b.cobs[b.T])
         b.compute_advantages_and_returns(last_values)
         s = self._stat.tolist()
         self._stat.zero_()

@@ -155,16 +155,19 @@ class VecShogiEnv:
 
     def step_rollout(self, actions: torch.Tensor, obs: Optional[torch.Tensor], bitmap: torch.Tensor,
                      reward: Optional[torch.Tensor] = None, done: Optional[torch.Tensor] = None,
-                     random_actions: bool = False, next_out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                     random_actions: bool = False, next_out: Optional[torch.Tensor] = None,
+                     cobs: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """``step`` in its rollout form (kz_step_rollout): the successor's legal set is written as the 13,527-bit legal
         bitmap (int32 [n, 448] rows, e.g. ``RolloutBuffer.bitmaps[t + 1]``) instead of the byte mask -- 1.8 KB instead
         of 13.5 KB per game here and in every later pass of the sampler / PPO update over it.  ``obs`` as in ``step``
-        (None: no observation rows); ``reward`` / ``done`` may point into rollout storage (fp32 / uint8 [n])."""
+        (None: no observation rows); ``reward`` / ``done`` may point into rollout storage (fp32 / uint8 [n]); ``cobs``
+        (int32 [n, 40]) receives the compact observations the policy network's input layer reads (kz_cobs_conv_*)."""
         if (actions.device != self.device or actions.dtype not in (torch.int64, torch.int32)
                 or not actions.is_contiguous() or actions.numel() < self.n):
             raise ValueError(f"actions: expected {self.n} contiguous int64/int32 policy indices on {self.device}")
         bp, bs = self._bitmap_args(bitmap)
         op, os_ = self._obs_args(obs)
+        cp = self._cobs_arg(cobs)
         reward = self.reward if reward is None else reward
         done = self.done if done is None else done
         for t, dt, what in ((reward, torch.float32, "reward"), (done, torch.uint8, "done")):
@@ -179,10 +182,10 @@ class VecShogiEnv:
                 raise ValueError("next_out must not alias actions (the kernel reads one while writing the other)")
         self.step_index += 1
         if self.step_streams > 1:
-            self._step_ranges(actions, op, os_, None, 0, bp, bs, reward, done, nxt)
+            self._step_ranges(actions, op, os_, None, 0, bp, bs, reward, done, nxt, cp)
         else:
             nv.check(self._L.kz_step_rollout(self.state.data_ptr(), self.n, self.hist_cap, actions.data_ptr(),
-                                             int(actions.dtype == torch.int64), op, os_, bp, bs, reward.data_ptr(),
+                                             int(actions.dtype == torch.int64), op, os_, bp, bs, cp, reward.data_ptr(),
                                              done.data_ptr(), self.reason.data_ptr(), self.winner.data_ptr(),
                                              self.ep_len.data_ptr(), self.legal_count.data_ptr(),
                                              nxt.data_ptr() if nxt is not None else None, self.seed, self.step_index,
@@ -190,7 +193,7 @@ class VecShogiEnv:
         return {"obs": obs, "bitmap": bitmap, "reward": reward, "done": done, "reason": self.reason,
                 "winner": self.winner, "ep_len": self.ep_len, "legal_count": self.legal_count}
 
-    def _step_ranges(self, actions, op, os_, mp, ms, bp, bs, reward, done, nxt) -> None:
+    def _step_ranges(self, actions, op, os_, mp, ms, bp, bs, reward, done, nxt, cp=None) -> None:
         """One step as ``step_streams`` concurrent kz_step_range launches over disjoint ranges of games (each with its own
         work counter), forked from and joined back into the current stream."""
         cur = torch.cuda.current_stream(self.device)
@@ -200,7 +203,7 @@ class VecShogiEnv:
         for i, st in enumerate(self._side_streams):
             st.wait_event(fork)
             nv.check(self._L.kz_step_range(self.state.data_ptr(), self.n, self.hist_cap, i * per, per, i, actions.data_ptr(),
-                                           int(actions.dtype == torch.int64), op, os_, mp, ms, bp, bs, reward.data_ptr(),
+                                           int(actions.dtype == torch.int64), op, os_, mp, ms, bp, bs, cp, reward.data_ptr(),
                                            done.data_ptr(), self.reason.data_ptr(), self.winner.data_ptr(),
                                            self.ep_len.data_ptr(), self.legal_count.data_ptr(),
                                            nxt.data_ptr() if nxt is not None else None, self.seed, self.step_index,
@@ -209,13 +212,22 @@ class VecShogiEnv:
             join.record(st)
             cur.wait_event(join)
 
-    def legal_bitmap(self, bitmap: torch.Tensor, obs: Optional[torch.Tensor] = None):
-        """Legal bitmap (and optionally the observation rows) of the CURRENT positions (kz_legal_bitmap)."""
+    def legal_bitmap(self, bitmap: torch.Tensor, obs: Optional[torch.Tensor] = None, cobs: Optional[torch.Tensor] = None):
+        """Legal bitmap (and optionally the observation rows / compact observations) of the CURRENT positions
+        (kz_legal_bitmap)."""
         bp, bs = self._bitmap_args(bitmap)
         op, os_ = self._obs_args(obs)
-        nv.check(self._L.kz_legal_bitmap(self.state.data_ptr(), self.n, self.hist_cap, op, os_, bp, bs,
+        nv.check(self._L.kz_legal_bitmap(self.state.data_ptr(), self.n, self.hist_cap, op, os_, bp, bs, self._cobs_arg(cobs),
                                          self.legal_count.data_ptr(), self._sp()), "kz_legal_bitmap")
         return obs, bitmap
+
+    def _cobs_arg(self, cobs: Optional[torch.Tensor]):
+        if cobs is None:
+            return None
+        if (cobs.device != self.device or cobs.dtype != torch.int32 or cobs.dim() != 2 or cobs.shape[0] < self.n
+                or cobs.shape[1] != nv.COBS_WORDS or not cobs.is_contiguous()):
+            raise ValueError(f"cobs: expected a contiguous int32 [{self.n}, {nv.COBS_WORDS}] tensor on {self.device}")
+        return cobs.data_ptr()
 
     def _bitmap_args(self, bitmap: torch.Tensor):
         if (bitmap.device != self.device or bitmap.dtype != torch.int32 or bitmap.dim() != 2 or bitmap.shape[0] < self.n

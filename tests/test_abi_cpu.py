@@ -97,18 +97,18 @@ def test_invalid_arguments_are_rejected_before_any_device_work():
     assert L.kz_step(z, 4, 500, z, 1, z, 0, z, 0, z, z, z, z, z, z, z, 0, 0, 0, 1, z) == -1
     assert L.kz_step_compact(z, 4, 500, z, 1, z, z, z, z, z, z, z, z, 0, 0, 0, 1, z) == -1
     assert L.kz_expand(z, 4, 500, z, z, 0, z, 0, z) == -1
-    assert L.kz_step_rollout(z, 4, 500, z, 1, z, 0, z, 448, z, z, z, z, z, z, z, 0, 0, 0, 1, z) == -1
-    assert L.kz_legal_bitmap(z, 4, 500, z, 0, z, 448, z, z) == -1
-    assert L.kz_step_range(z, 4, 500, 0, 2, 0, z, 1, z, 0, z, 0, z, 0, z, z, z, z, z, z, z, 0, 0, 0, 1, z) == -1
+    assert L.kz_step_rollout(z, 4, 500, z, 1, z, 0, z, 448, z, z, z, z, z, z, z, z, 0, 0, 0, 1, z) == -1
+    assert L.kz_legal_bitmap(z, 4, 500, z, 0, z, 448, z, z, z) == -1
+    assert L.kz_step_range(z, 4, 500, 0, 2, 0, z, 1, z, 0, z, 0, z, 0, z, z, z, z, z, z, z, z, 0, 0, 0, 1, z) == -1
     assert L.kz_bitmap_expand(z, 448, z, 4, z, 13536, z) == -1
-    assert L.kz_sample_bitmap(z, 0, 13527, z, 448, 4, 0, 0, z, 1, z, z, 0, z) == -1
+    assert L.kz_sample_bitmap(z, 0, 13527, z, 448, 4, 0, 0, z, z, 1, z, z, 0, z) == -1
     assert L.kz_eval_bitmap_fwd(z, 0, 13527, z, 448, z, z, 4, z, z, z, z) == -1
     assert L.kz_eval_bitmap_bwd(z, 0, 13527, z, 448, z, z, 4, z, z, z, z, 13536, z, z) == -1
     assert L.kz_legal_mask(z, 4, 500, z, 0, z, z) == -1
     assert L.kz_observe(z, 4, 500, z, 0, z) == -1
     assert L.kz_piece_targets(z, 4, 500, z, z, z) in bad
     assert L.kz_errors(z, 4, 500, z, 0, z) in bad
-    assert L.kz_sample_masked(z, 0, 13527, z, 13527, 4, 0, 0, z, 1, z, z, 0, z) == -1
+    assert L.kz_sample_masked(z, 0, 13527, z, 13527, 4, 0, 0, z, z, 1, z, z, 0, z) == -1
     assert L.kz_gae(z, z, z, z, 8, 4, 0.99, 0.94, z, z, z) == -1
     assert L.kz_gae_exact(z, z, z, z, 8, 4, 0.99, 0.94, z, z, z) == -1
     assert L.kz_eval_masked_fwd(z, 0, 13527, z, 13527, z, z, 4, z, z, z, z) == -1
@@ -118,4 +118,6 @@ def test_invalid_arguments_are_rejected_before_any_device_work():
     assert L.kz_obs_conv_fwd(z, z, z, z, 16, 4, 1, z, z) == -1
     assert L.kz_obs_conv_wgrad(z, z, z, z, 1, 16, 4, z, 1, z, z, z) == -1
     assert L.kz_adam_clip_step(0, z, z, z, z, z, z, 3e-4, 0.9, 0.999, 1e-8, 0.0, 0.5, z, 0, z, z) == -1
+    assert L.kz_cobs_conv_fwd(z, z, z, z, 16, 4, 1, z, z) == -1
+    assert L.kz_cobs_conv_wgrad(z, z, z, z, 1, 16, 4, z, 1, z, z, z) == -1
     assert L.kz_obs_conv_wgrad_ctas(0) <= 0 or L.kz_obs_conv_wgrad_ctas(1) >= 1

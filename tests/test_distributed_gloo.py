@@ -63,11 +63,12 @@ def _worker(rank, world, port, out):
         ps = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2, 2))]
         for i, prm in enumerate(ps):
             prm.grad = torch.full_like(prm, float(10 * rank + i))
-        ps[0].grad = red.early(ps[0].grad)
+        g0, ps[0].grad = ps[0].grad, None
+        red.early(ps[0], g0)
         red.finish(ps)
         for i, prm in enumerate(ps):
             assert torch.equal(prm.grad, torch.full_like(prm, float(10 * sum(range(world)) + world * i))), (i, prm.grad)
-        assert not red._pending and not red._early_ids
+        assert not red._events and not red._early
         # a model without the fused path is wrapped in DistributedDataParallel: same property through the wrapper
         from shogidrl_b200.core.base_actor_critic import ActorCriticResTower
         torch.manual_seed(rank)  # different initial weights per rank: the wrapper broadcasts rank 0's

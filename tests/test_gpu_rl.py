@@ -488,3 +488,113 @@ def test_policy_head_bias_gradient_is_deterministic_and_matches_column_sums():
     ((dist.log_prob(act) * wl).sum() + 0.01 * dist.entropy().sum()).backward()
     ref_db = logits.grad.sum(0)
     assert torch.allclose(grads[0][0], ref_db, rtol=2e-3, atol=2e-3 * float(ref_db.abs().max()))
+
+
+# ------------------------------------------------------------------------------------------------
+# compact observations (kz_step_rollout's cobs output) and the input layer that reads them (kz_cobs_conv_*)
+def _obs_from_cobs(cobs):
+    """int32 [n, 40] compact observations -> fp32 [n, 46, 9, 9] (what they summarise), in plain torch."""
+    n = cobs.shape[0]
+    by = cobs.view(torch.uint8).reshape(n, 160)
+    planes = by[:, :81].long()
+    obs = torch.zeros((n, 46, 81), dtype=torch.float32, device=cobs.device)
+    has = planes < 28
+    idx = torch.nonzero(has)
+    obs[idx[:, 0], planes[has], idx[:, 1]] = 1.0
+    pv = cobs[:, 21:39].contiguous().view(torch.float32)
+    obs[:, 28:46, :] = pv[:, :, None]
+    return obs.reshape(n, 46, 9, 9)
+
+
+def _rollout_positions(n=2048, T=40):
+    from shogidrl_b200 import VecShogiEnv
+    dev = torch.device("cuda:0")
+    env = VecShogiEnv(n, max_moves_per_game=60, device=dev, seed=17)
+    obs = torch.zeros((T + 1, n, 46, 9, 9), dtype=torch.float32, device=dev)
+    bm = torch.zeros((T + 1, n, 448), dtype=torch.int32, device=dev)
+    cobs = torch.full((T + 1, n, 40), -7, dtype=torch.int32, device=dev)
+    acts = [torch.zeros(n, dtype=torch.int64, device=dev) for _ in range(2)]
+    env.refresh(random_actions=True, next_out=acts[0])
+    env.legal_bitmap(bm[0], obs=obs[0], cobs=cobs[0])
+    for t in range(T):
+        env.step_rollout(acts[t & 1], obs[t + 1], bm[t + 1], random_actions=True, next_out=acts[(t + 1) & 1], cobs=cobs[t + 1])
+    return obs.reshape(-1, 46, 9, 9), cobs.reshape(-1, 40)
+
+
+def test_compact_observation_is_the_observation():
+    """The 160-byte compact observation the engine writes beside every observation row decodes to exactly that row
+    (piece-plane index per square, rotated for White to move, + the 18 constant-plane values), across resets."""
+    obs, cobs = _rollout_positions()
+    assert torch.equal(_obs_from_cobs(cobs), obs)
+    assert bool((cobs.view(torch.uint8).reshape(-1, 160)[:, 81:84] == 0xFF).all())  # pad bytes of the square table
+    side_black = obs[:, 42, 0, 0] == 1.0
+    assert bool(side_black.any()) and bool((~side_black).any())  # both perspectives occur
+
+
+@pytest.mark.parametrize("relu", [True, False])
+def test_input_layer_from_compact_observations(relu):
+    """kz_cobs_conv_fwd (sparse: nine weight look-ups per output + constant planes, no dense product) and
+    kz_cobs_conv_wgrad (tensor-core tile patched from the compact observation) against the dense kernels reading the
+    fp32 rows of the same positions and against torch's conv2d on bf16-rounded operands; rows gathered in place."""
+    from shogidrl_b200 import nn_ops
+    dev = torch.device("cuda:0")
+    obs, cobs = _rollout_positions(1024, 30)
+    g = torch.Generator(device="cpu").manual_seed(4)
+    w = (torch.randn(16, 46, 3, 3, generator=g) * 0.05).to(dev).requires_grad_(True)
+    b = (torch.randn(16, generator=g) * 0.1).to(dev).requires_grad_(True)
+    rows = torch.randperm(obs.shape[0], device=dev)[:5000]
+    y_c = nn_ops.obs_conv(obs, w, b, relu=relu, rows=rows, cobs=cobs)
+    y_d = nn_ops.obs_conv(obs, w, b, relu=relu, rows=rows)
+    ref = torch.nn.functional.conv2d(obs[rows].bfloat16().float(), w.detach().bfloat16().float(), b.detach().bfloat16().float(), padding=1)
+    ref = torch.relu(ref) if relu else ref
+    scale = float(ref.abs().max())
+    assert float((y_c.float() - ref).abs().max()) <= 2.0 ** -7 * scale + 1e-3   # bf16 output rounding
+    assert float((y_c.float() - y_d.float()).abs().max()) <= 2.0 ** -7 * scale + 1e-3
+    assert float((y_c.float() - y_d.float()).abs().mean()) <= 1e-4 * scale           # almost always the same bf16 value
+    dy = torch.randn(y_c.shape, generator=torch.Generator(device="cpu").manual_seed(5)).to(dev).bfloat16()
+    gw_c, gb_c = torch.autograd.grad(y_c, (w, b), dy, retain_graph=True)
+    gw_d, gb_d = torch.autograd.grad(y_d, (w, b), dy, retain_graph=True)
+    # the two weight-gradient kernels multiply the same bf16 tiles: equal up to the order of the per-CTA partial sums
+    assert torch.allclose(gw_c, gw_d, rtol=1e-4, atol=1e-4 * float(gw_d.abs().max()))
+    assert torch.allclose(gb_c, gb_d, rtol=1e-4, atol=1e-4 * float(gb_d.abs().max()))
+    # without row indices, and a batch smaller than one CTA wave
+    y1 = nn_ops.obs_conv(obs[:37], w, b, relu=relu, cobs=cobs[:37].contiguous())
+    assert float((y1.float() - nn_ops.obs_conv(obs[:37], w, b, relu=relu).float()).abs().max()) <= 2.0 ** -7 * scale + 1e-3
+
+
+def test_ppo_update_reads_compact_observations():
+    """PPOAgent.learn over a RolloutBuffer feeds the input layer from the compact observations; the same update from the
+    fp32 observation rows (compact form withheld) gives the same metrics and parameters within bf16 tolerance."""
+    from shogidrl_b200 import VecShogiEnv
+    from shogidrl_b200.core import ActorCritic, PPOAgent, RolloutBuffer
+    from shogidrl_b200.training import VecStepManager
+    from tests.helpers import make_config
+    dev = torch.device("cuda")
+    N, T = 512, 8
+
+    def run(withhold):
+        cfg = make_config(minibatch_size=1024, ppo_epochs=2)
+        torch.manual_seed(1)
+        env = VecShogiEnv(N, max_moves_per_game=40, device=dev, seed=5)
+        agent = PPOAgent(ActorCritic(46, 13527), cfg, dev, use_mixed_precision=True)
+        agent.model.sample_seed = 99
+        buf = RolloutBuffer(T, N, 0.99, 0.95, dev)
+        drv = VecStepManager(env, agent, buf)
+        drv.collect(); drv.finish()
+        if withhold:
+            full = buf.get_batch
+            buf.get_batch = lambda: {k: v for k, v in full().items() if k != "compact_obs"}
+        m = agent.learn(buf)
+        return m, [p.detach().clone() for p in agent.model.parameters()], buf.actions.clone()
+
+    import shogidrl_b200.core.base_actor_critic as bac
+    import itertools
+    bac._sample_counter = itertools.count()
+    m1, p1, a1 = run(False)
+    bac._sample_counter = itertools.count()
+    m2, p2, a2 = run(True)
+    assert torch.equal(a1, a2)  # the rollouts agree action for action (same sampler stream, logits equal up to bf16 ties)
+    for k in m1:
+        assert abs(m1[k] - m2[k]) <= 2e-3 * max(1.0, abs(m2[k])), (k, m1[k], m2[k])
+    for x, y in zip(p1, p2):
+        assert torch.allclose(x, y, rtol=1e-3, atol=2e-4), float((x - y).abs().max())
