@@ -772,7 +772,8 @@ def measure_ppo(args, dev, world, rank, barrier):
                                  entropy_coef=0.01, ppo_epochs=args.ppo_epochs, minibatch_size=mb, steps_per_epoch=N * T,
                                  total_timesteps=N * T * 8, gradient_clip_max_norm=0.5, normalize_advantages=True,
                                  enable_value_clipping=False, weight_decay=0.0, lr_schedule_type=None,
-                                 lr_schedule_step_on="epoch", lr_schedule_kwargs=None),
+                                 lr_schedule_step_on="epoch", lr_schedule_kwargs=None,
+                                 cuda_graph_rollout=not args.no_graph_rollout),
         display=SimpleNamespace(display_moves=False, turn_tick=0.0))
     torch.manual_seed(SEED + rank)
     if args.ppo_model == "resnet":
@@ -780,7 +781,8 @@ def measure_ppo(args, dev, world, rank, barrier):
     else:
         model = ActorCritic(46, 13527)
     tr = SelfPlayTrainer(model, cfg, N, T, dev, use_mixed_precision=True)
-    for _ in range(max(2, args.ppo_warmup)):  # epoch 1 captures the update graph, epoch 2 the rollout graph
+    warm = max(1 if args.no_graph_rollout else 2, args.ppo_warmup)  # epoch 1 captures the update graph, epoch 2 the rollout graph
+    for _ in range(warm):
         tr.run_epoch()
     barrier()
     sampler = ClockSampler(dev.index or 0)
@@ -852,11 +854,12 @@ def measure_ppo(args, dev, world, rank, barrier):
         cnn = args.ppo_model == "cnn"
         rb = rollout_bytes_per_sample(mean_ply)
         rec = {"metric": "PPO self-play samples/sec", "value": samples / (total_ms * 1e-3), "unit": "samples/s",
-               "n_gpus": world, "steps": steps, "warmup": max(2, args.ppo_warmup), "ms_per_step": total_ms / steps,
+               "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": total_ms / steps,
                "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
                "config": {"workload": f"BASELINE config {3 if cnn else 4}: PPO self-play, {args.ppo_model} policy-value net "
                                       f"(bf16 autocast), {N} envs/GPU, T={T}, fused masked sampling on legal bitmaps + device "
-                                      f"GAE, ppo_epochs={args.ppo_epochs}, minibatch={mb} ({n_upd} updates per epoch)",
+                                      f"GAE, ppo_epochs={args.ppo_epochs}, minibatch={mb} ({n_upd} updates per epoch)"
+                                      + (", eager rollout loop" if args.no_graph_rollout else ", rollout replayed from a CUDA graph"),
                           "envs_per_gpu": N, "horizon": T, "minibatch": mb, "ppo_epochs": args.ppo_epochs,
                           "parallelism": f"env-shard x{world}, gradient all-reduce over NCCL in the update" if world > 1 else "1 GPU",
                           "rollout_storage_gb": (b.obs.numel() * 4 + b.bitmaps.numel() * 4) / 1e9},
@@ -945,6 +948,7 @@ def main():
     ap.add_argument("--ref-ppo-steps", type=int, default=512, help="timesteps per epoch of the CPU PPO reference arm")
     ap.add_argument("--ref-same-minibatch", action="store_true", help="--impl reference --workload ppo: minibatch = min(--ppo-minibatch, steps) instead of the reference's 64")
     ap.add_argument("--no-ppo", action="store_true", help="skip the PPO (config 3) record of the default workload")
+    ap.add_argument("--no-graph-rollout", action="store_true", help="run the rollout loop eagerly (one warm-up epoch suffices then)")
     ap.add_argument("--ppo-steps", type=int, default=2, help="timed PPO epochs of the `ppo` record")
     ap.add_argument("--ppo-warmup", type=int, default=2, help="untimed PPO epochs (the first captures the update graph, the second the rollout graph)")
     args = ap.parse_args()
