@@ -55,6 +55,13 @@ class PPOAgent:
         self.scaler = scaler
         self.use_mixed_precision = use_mixed_precision
         self.model = model.to(self.device)
+        if self.device.type == "cuda" and getattr(self.model, "prefers_channels_last", False):
+            self.model.to(memory_format=torch.channels_last)  # before the optimizer / DDP wrapper look at the parameters
+            for p in self.model.parameters():
+                # 1x1 kernels are the same bytes in both layouts: keep the default strides, which is how autograd lays out
+                # their gradients (DDP's bucket views compare strides)
+                if p.dim() == 4 and tuple(p.shape[2:]) == (1, 1):
+                    p.data = torch.empty_like(p, memory_format=torch.contiguous_format).copy_(p)
         self.policy_output_mapper = PolicyOutputMapper()
         self.num_actions_total = self.policy_output_mapper.get_total_actions()
         tr = config.training
@@ -106,11 +113,14 @@ class PPOAgent:
 
     def select_actions(self, obs: torch.Tensor, legal_mask: torch.Tensor, *, is_training: bool = True,
                        out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, cobs: Optional[torch.Tensor] = None,
-                       draw_counter: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                       draw_counter: Optional[torch.Tensor] = None, eval_mode: bool = False
+                       ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """Batched select_action: obs [N,46,9,9] and legal_mask [N,13527] (or the engine's legal bitmap rows, int32
         [N,448]) stay on the device; returns (actions int64 [N], log_probs fp32 [N], values fp32 [N]) without any
         host synchronisation.  ``out`` = (actions, log_probs) rows of the rollout storage to write into."""
-        self.model.train(is_training)
+        # eval_mode: sample (is_training) from a network in eval() -- what the reference's self-play workers do
+        # (training/parallel/self_play_worker.py:130, 190-214)
+        self.model.train(is_training and not eval_mode)
         kw = {"out": out} if out is not None else {}
         if cobs is not None and not self._is_obs_scaler():
             kw["cobs"] = cobs  # the engine's compact observations of `obs` (input layers that read them skip the 14.9 KB rows)

@@ -198,6 +198,29 @@ def evaluate_tournament(agent, opponents: Mapping[str, Any], num_games_per_oppon
     return tournament_standings(results), results
 
 
+def benchmark_performance(results: Mapping[str, EvaluationResult]) -> Dict[str, Any]:
+    """The reference's benchmark analytics (keisei/evaluation/strategies/benchmark.py:639-686) from per-case match results:
+    a case is "passed" by a game the agent wins; cases without games report the reference's empty record."""
+    per: Dict[str, Dict[str, Any]] = {}
+    for name, r in results.items():
+        if r.games == 0:
+            per[name] = {"played": 0, "wins_or_passes": 0, "pass_rate": 0, "details": "No games played"}
+        else:
+            per[name] = {"played": r.games, "wins_or_passes": r.agent_wins, "pass_rate": r.agent_wins / r.games}
+    played = sum(p["played"] for p in per.values())
+    overall = sum(p["wins_or_passes"] for p in per.values()) / played if played else 0
+    return {"per_benchmark_case_results": per, "overall_benchmark_pass_rate": overall}
+
+
+def evaluate_benchmark(agent, suite: Mapping[str, Any], num_games_per_case: int,
+                       **kwargs) -> Tuple[Dict[str, Any], Dict[str, EvaluationResult]]:
+    """The benchmark strategy (benchmark.py:330-426, 556-637) on the vectorised engine: ``num_games_per_case`` games against
+    every case of the suite (name -> opponent agent, or None for the uniform-random baseline the reference's default suite
+    starts with), colours balanced; returns (the reference's performance dictionary, per-case results)."""
+    results = {name: evaluate_vs_opponent(agent, num_games_per_case, opponent=opp, **kwargs) for name, opp in suite.items()}
+    return benchmark_performance(results), results
+
+
 def select_ladder_opponents(agent_rating: float, pool_ratings: Mapping[str, float], num_opponents_to_select: int = 5,
                             window: float = 400.0) -> List[str]:
     """ladder.py:700-732: opponents rated within +-400 of the agent, ascending by rating, the first N."""

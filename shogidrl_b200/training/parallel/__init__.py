@@ -62,12 +62,19 @@ class ParallelManager:
         self.is_running = False
         self._driver: Optional[VecStepManager] = None
 
-    def start_workers(self, agent, gamma: float = 0.99, lambda_gae: float = 0.95) -> bool:
+    def start_workers(self, agent, gamma: float = 0.99, lambda_gae: float = 0.95, worker_semantics: bool = True) -> bool:
+        """``worker_semantics`` keeps what distinguishes the reference's worker processes from its main loop
+        (self_play_worker.py:105, 130, 190-214): every worker game is a ``ShogiGame()`` with the DEFAULT 500-move limit
+        whatever ``env.max_moves_per_game`` says, and actions are sampled from the network in ``eval()`` mode.  (Its
+        masking formula, softmax(all logits) * mask / (sum + 1e-8) handed to ``Categorical(probs=...)``, is the masked
+        softmax the sampler draws from: Categorical renormalises, so the 1e-8 cancels.)"""
         from ...vec_env import VecShogiEnv
-        env = VecShogiEnv(self.num_workers, max_moves_per_game=int(self.env_config.get("max_moves_per_game", 500)),
+        max_moves = 500 if worker_semantics else int(self.env_config.get("max_moves_per_game", 500))
+        env = VecShogiEnv(self.num_workers, max_moves_per_game=max_moves,
                           device=self.device, seed=int(self.env_config.get("seed", 0) or 0))
         buf = RolloutBuffer(self.batch_size, self.num_workers, gamma, lambda_gae, self.device)
         self._driver = VecStepManager(env, agent, buf)
+        self._driver.model_eval_mode = bool(worker_semantics)
         self._driver.start()
         self.is_running = True
         return True

@@ -229,6 +229,7 @@ class VecStepManager:
         self.graph_rollout = bool(getattr(tr, "cuda_graph_rollout", True))
         self._graph = None
         self._eager_runs = 0
+        self.model_eval_mode = False  # True: sample from the network in eval() (the reference's worker processes)
 
     def start(self) -> None:
         self.env.reset(refresh=False)
@@ -271,7 +272,7 @@ class VecStepManager:
         for t in range(b.T):
             _, _, value = self.agent.select_actions(b.obs[t], b.bitmaps[t], is_training=True,
                                                     out=(b.actions[t], b.log_probs[t]), cobs=b.cobs[t],
-                                                    draw_counter=self._draws)
+                                                    draw_counter=self._draws, eval_mode=self.model_eval_mode)
             b.values[t].copy_(value)
             out = env.step_rollout(b.actions[t], b.obs[t + 1], b.bitmaps[t + 1], reward=b.rewards[t], done=b.dones[t],
                                    cobs=b.cobs[t + 1])

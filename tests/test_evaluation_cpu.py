@@ -5,8 +5,8 @@ import os
 
 import pytest
 
-from shogidrl_b200.evaluation import (EloRegistry, EloTracker, EvaluationResult, select_ladder_opponents,
-                                      tournament_standings)
+from shogidrl_b200.evaluation import (EloRegistry, EloTracker, EvaluationResult, benchmark_performance,
+                                      select_ladder_opponents, tournament_standings)
 
 
 @pytest.fixture(scope="module")
@@ -48,3 +48,15 @@ def test_ladder_selection_matches_reference(golden):
         pool = {name: rating for name, rating in case["pool"]}
         assert select_ladder_opponents(case["agent_rating"], pool, case["num"]) == case["selected"]
     assert select_ladder_opponents(1500.0, {}) == []
+
+
+def test_benchmark_performance_schema():
+    """benchmark.py:639-686: per-case played / wins_or_passes / pass_rate, the empty-case record, the overall pass rate."""
+    res = {"benchmark_random": EvaluationResult(10, 7, 2, 1, 0.0), "benchmark_heuristic": EvaluationResult(4, 1, 3, 0, 0.0),
+           "unplayed": EvaluationResult(0, 0, 0, 0, 0.0)}
+    perf = benchmark_performance(res)
+    assert perf["per_benchmark_case_results"]["benchmark_random"] == {"played": 10, "wins_or_passes": 7, "pass_rate": 0.7}
+    assert perf["per_benchmark_case_results"]["unplayed"] == {"played": 0, "wins_or_passes": 0, "pass_rate": 0,
+                                                               "details": "No games played"}
+    assert perf["overall_benchmark_pass_rate"] == 8 / 14
+    assert benchmark_performance({})["overall_benchmark_pass_rate"] == 0

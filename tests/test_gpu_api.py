@@ -210,8 +210,14 @@ def test_parallel_manager_shim():
     buf = ExperienceBuffer(100, 0.99, 0.95, "cuda")
     assert pm.collect_experiences(buf) == 32 and pm.collect_experiences(buf) == 32 and len(buf) == 64
     assert bool(buf.legal_masks[:64].gather(1, buf.actions[:64, None]).all())
+    # worker semantics (self_play_worker.py:105, 130): 500-move games whatever the env config says, network in eval()
+    assert pm._driver.env.max_moves == 500 and pm._driver.model_eval_mode and not agent.model.training
     pm.stop_workers()
     assert not pm.is_healthy() and pm.get_parallel_stats()["total_steps_collected"] == 64
+    pm2 = ParallelManager({"max_moves_per_game": 40, "seed": 3}, {}, {"num_workers": 8, "batch_size": 4}, "cuda")
+    pm2.start_workers(agent, worker_semantics=False)
+    assert pm2._driver.env.max_moves == 40 and pm2.collect_experiences(ExperienceBuffer(100, 0.99, 0.95, "cuda")) == 32
+    assert agent.model.training
 
 
 def test_agent_matches_reference_golden(golden_dir):
@@ -338,6 +344,13 @@ def test_tournament_and_ladder_on_the_vectorised_engine():
     for name, r in results.items():
         row = standings["per_opponent_results"][name]
         assert (row["played"], row["wins"], row["losses"], row["draws"]) == (r.games, r.agent_wins, r.opponent_wins, r.draws)
+    from shogidrl_b200.evaluation import evaluate_benchmark
+    perf, cases = evaluate_benchmark(agent, {"benchmark_random": None, "benchmark_other": other}, 16, **kw)
+    assert set(perf["per_benchmark_case_results"]) == {"benchmark_random", "benchmark_other"}
+    for name, r in cases.items():
+        row = perf["per_benchmark_case_results"][name]
+        assert (row["played"], row["wins_or_passes"]) == (16, r.agent_wins) and row["pass_rate"] == r.agent_wins / 16
+    assert perf["overall_benchmark_pass_rate"] == sum(r.agent_wins for r in cases.values()) / 32
     tracker = EloTracker()
     tracker.ratings.update({"random": 1400.0, "other": 1500.0, "far": 2200.0})
     snap, played = evaluate_ladder(agent, "agent", {"random": None, "other": other, "far": other}, tracker,
