@@ -200,7 +200,13 @@ def adam_clip_applicable(optimizer: torch.optim.Optimizer) -> bool:
     g = optimizer.param_groups[0]
     if g.get("amsgrad") or g.get("maximize") or g.get("differentiable") or isinstance(g["lr"], torch.Tensor):
         return False
-    return all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and not p.is_sparse for p in g["params"])
+    return all(p.is_cuda and p.dtype == torch.float32 and _dense(p) and not p.is_sparse for p in g["params"])
+
+
+def _dense(t: torch.Tensor) -> bool:
+    """Non-overlapping and dense in either memory format: the update is elementwise over the storage, so any such layout
+    works as long as parameter, gradient and moments share it (channels_last convolution weights of the ResNet tower)."""
+    return t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last))
 
 
 def adam_clip_step(optimizer: torch.optim.Adam, max_norm: float, norm_out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -225,7 +231,12 @@ def adam_clip_step(optimizer: torch.optim.Adam, max_norm: float, norm_out: Optio
             st["step"] = torch.as_tensor(float(st["step"]), dtype=torch.float32, device=dev)  # loaded non-capturable state
         steps.append(st["step"])
         g = p.grad
-        grads.append(g if g.dtype == torch.float32 and g.is_contiguous() else g.float().contiguous())
+        if g.dtype != torch.float32 or g.stride() != p.stride():
+            g = torch.empty_like(p, memory_format=torch.preserve_format).copy_(g)  # the parameter's layout, fp32
+        grads.append(g)
+        for k in ("exp_avg", "exp_avg_sq"):
+            if st[k].stride() != p.stride():  # e.g. state loaded from a checkpoint written in the other layout
+                st[k] = torch.empty_like(p, memory_format=torch.preserve_format).copy_(st[k])
     torch._foreach_add_(steps, 1.0)
     n = len(params)
     numel = (C.c_int64 * n)(*[p.numel() for p in params])

@@ -356,10 +356,14 @@ def test_fused_clip_adam_matches_torch(weight_decay, max_norm):
     from shogidrl_b200 import rl
     dev = torch.device("cuda:0")
     g = torch.Generator(device="cpu").manual_seed(5)
-    shapes = [(1353, 129), (16, 46, 3, 3), (4096,), (7,), (1,), (3, 4099)]
+    shapes = [(1353, 129), (16, 46, 3, 3), (4096,), (7,), (1,), (3, 4099), (32, 24, 3, 3)]
     base = [torch.randn(s, generator=g) for s in shapes]
     pa = [torch.nn.Parameter(b.clone().to(dev)) for b in base]
     pb = [torch.nn.Parameter(b.clone().to(dev)) for b in base]
+    # the last tensor lives in channels_last memory (the ResNet tower's convolution weights) and gets default-layout
+    # gradients: the fused tail pairs elements by their logical index, not by their position in the storage
+    pa[-1].data = pa[-1].data.contiguous(memory_format=torch.channels_last)
+    assert not pa[-1].is_contiguous()
     kw = dict(lr=3e-4, weight_decay=weight_decay, capturable=True)
     oa, ob = torch.optim.Adam(pa, **kw), torch.optim.Adam(pb, **kw)
     assert rl.adam_clip_applicable(oa)
