@@ -6,7 +6,7 @@ for f in ${VARIANTS:-build/*/*.so}; do
   if [ "${TESTS:-0}" = "1" ]; then
     KZ_LIB_PATH=$PWD/$f timeout 300 python -m pytest tests/test_gpu_engine.py -x -q 2>&1 | tail -2
   fi
-  KZ_LIB_PATH=$PWD/$f timeout 120 python bench.py --steps ${STEPS:-128} --warmup 8 --no-cpu-baseline 2>&1 | python -c "
+  KZ_LIB_PATH=$PWD/$f timeout 120 python bench.py --steps ${STEPS:-128} --warmup 8 --no-cpu-baseline --no-ppo 2>&1 | python -c "
 import sys,json
 for ln in sys.stdin:
     try: d=json.loads(ln)

@@ -642,13 +642,21 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
   // measured 0.387 -> 0.375 ms; barriers at more points cost more in waiting than they save); (2) tiles after the
   // first are claimed from a global counter instead of a fixed stride, so CTAs that drew cheap positions take more
   // tiles and the grid drains together (a static split leaves 200 of 444 CTAs one game longer than the rest, and
-  // the kernel as slow as its unluckiest CTA).  Thread 0 claims two tiles ahead: the id for game i + 1 is needed
-  // at the top of game i for the prefetch, so it is fetched during game i - 1 and handed over through s_tile.
+  // the kernel as slow as its unluckiest CTA).  The id for game i + 1 is needed at the top of game i for the prefetch,
+  // so claims run ahead of the games (see s_tile below).
   const bool lockstep = (P.n % WARPS_PER_CTA) == 0 && P.tile_counter != nullptr;
   const int ntiles = P.n / WARPS_PER_CTA;
-  __shared__ int s_tile[2];
-  int tile = blockIdx.x, claimed = 0;
-  if (lockstep && threadIdx.x == 0) s_tile[1] = gridDim.x + atomicAdd(P.tile_counter, 1);
+  // Claims are pipelined three tiles deep: the atomic for the tile of iteration it + 3 is issued at the END of iteration
+  // it, its result is stored to s_tile at the top of iteration it + 1 (behind the barrier, whose wait hides the round
+  // trip) and read by every warp at the top of iteration it + 2.  (Issued at the loop top and kept until the loop end, the
+  // result was spilled to local memory under the 80-register cap: the claiming warp stalled on the atomic at the spill and
+  // again on the reload behind the row stores -- 10 % of its samples -- and the whole CTA waited for it at the barrier.)
+  __shared__ int s_tile[4];
+  int tile = blockIdx.x, pending = 0;
+  if (lockstep && threadIdx.x == 0) {
+    s_tile[1] = gridDim.x + atomicAdd(P.tile_counter, 1);
+    pending = gridDim.x + atomicAdd(P.tile_counter, 1);  // the tile of iteration 2
+  }
   const int g_stride = gridDim.x * WARPS_PER_CTA;
   int g = P.g_first + blockIdx.x * WARPS_PER_CTA + warp;
   uint32_t next_word = fetch_state(g);
@@ -659,9 +667,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
     int g_next = g + g_stride;
     if (lockstep) {
       __syncthreads();
-      tile = s_tile[(it + 1) & 1];  // the tile after this one
+      tile = s_tile[(it + 1) & 3];  // the tile after this one
       g_next = P.g_first + tile * WARPS_PER_CTA + warp;
-      if (threadIdx.x == 0) claimed = gridDim.x + atomicAdd(P.tile_counter, 1);  // two ahead; stored at the loop end
+      if (threadIdx.x == 0) s_tile[(it + 2) & 3] = pending;  // claimed at the end of the previous iteration
     }
     // ---- state of this game (prefetched), start fetching the next one
     __syncwarp();
@@ -1077,9 +1085,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
           // compose-once writer: 32-byte piece q of the row = the 32 actions of bitmap word q (pad bytes 13527..13535
           // are written as zeros: the bitmap is zero-padded)
           __syncwarp();
-#pragma unroll 1
-          for (int q = lane; q < 423; q += 32) {
-            const uint32_t w = ws.bitmap[q];
+          auto piece = [&](int q, uint32_t w) {
             if (w == 0) st_zero256(mrow + 32 * q);
             else {
               uint32_t v[8];
@@ -1087,7 +1093,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
               for (int k = 0; k < 8; k++) v[k] = (((w >> (4 * k)) & 0xF) * 0x00204081u) & 0x01010101u;
               st256(mrow + 32 * q, v);
             }
-          }
+          };
+          // (two pieces per round, both bitmap words loaded before either is tested: measured 0.3494 vs 0.3473 ms, not kept)
+#pragma unroll 1
+          for (int q = lane; q < 423; q += 32) piece(q, ws.bitmap[q]);
           return;
         }
 #endif
@@ -1280,7 +1289,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
       else mdst[lane - 24] = reinterpret_cast<uint32_t*>(ws.meta)[lane - 24];
     }
     __syncwarp();
-    if (lockstep && threadIdx.x == 0) s_tile[it & 1] = claimed;  // read after the next barrier as tile it + 2
+    if (lockstep && threadIdx.x == 0) pending = gridDim.x + atomicAdd(P.tile_counter, 1);  // the tile of iteration it + 3
     g = g_next;
   }
 #if KZ_BULK_ZERO
