@@ -13,6 +13,7 @@
 // checker / pin / king-danger bitboards built with warp ballots (lane l owns squares l, l+32, l+64, so
 // a ballot over slot j IS word j of an 81-bit bitboard).  tests/ check the two against each other.
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 #include "../../include/keisei_b200.h"
 #include "kz_common.cuh"
@@ -626,10 +627,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
 
   // One 32-bit word of game state per lane (lanes 0-23: board, 24-31: meta) and the action are fetched one
   // game ahead, so that their DRAM latency overlaps the previous game's work.
+  // (One load with a per-lane address, not one load per branch: the two branches of a divergent `lane < 24 ? board :
+  // meta` write the same destination register, and the register scoreboard is per warp -- the second branch's use of the
+  // OLD value then waits for the first branch's just-issued load, a full DRAM round trip per game: 5.6 % of all samples in
+  // the round-2 line attribution.)
   auto fetch_state = [&](int g) -> uint32_t {
     if (g >= g_end) return 0u;
-    return lane < 24 ? reinterpret_cast<const uint32_t*>(P.boards + (size_t)g * 96)[lane]
-                     : reinterpret_cast<const uint32_t*>(P.meta + (size_t)g * 32)[lane - 24];
+    const uint8_t* src = lane < 24 ? P.boards + (size_t)g * 96 + 4 * lane : P.meta + (size_t)g * 32 + 4 * (lane - 24);
+    return *reinterpret_cast<const uint32_t*>(src);
   };
   auto fetch_action = [&](int g) -> long long {
     if (g >= g_end || MODE == 0) return 0;
@@ -673,8 +678,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MIN_CTAS_PER_SM) kz_step_k
     }
     // ---- state of this game (prefetched), start fetching the next one
     __syncwarp();
-    if (lane < 24) reinterpret_cast<uint32_t*>(ws.board)[lane] = next_word;
-    else reinterpret_cast<uint32_t*>(ws.meta)[lane - 24] = next_word;
+    static_assert(offsetof(WarpScratch, meta) == offsetof(WarpScratch, board) + 96, "meta must follow board: one store for all 32 lanes");
+    reinterpret_cast<uint32_t*>(ws.board)[lane] = next_word;  // lanes 0-23: board words, 24-31: the meta row right behind it
     const long long a = next_action;
     next_word = fetch_state(g_next);
     next_action = fetch_action(g_next);
