@@ -1,0 +1,29 @@
+"""Copy the reference's own hot-path test files into baseline/_ref_tests/ (git-ignored, like baseline/_ref) so that they
+travel to the GPU box with the tree, where tests/test_gpu_reference_suite.py runs them unmodified against this repository's
+classes through the keisei -> shogidrl_b200 alias package (tests/ref_alias).  Run in a container that has the checkout:
+
+    python tests/fetch_reference_tests.py [/root/reference]
+
+The copies are never committed (the reference's sources do not belong in this repository)."""
+import os
+import shutil
+import sys
+
+FILES = ["test_legal_mask_generation.py", "test_shogi_rules_and_validation.py", "test_shogi_game_core_logic.py",
+         "test_shogi_engine_integration.py", "test_shogi_game_rewards.py", "test_shogi_utils.py",
+         "test_observation_constants.py", "test_reward_with_flipped_perspective.py"]
+
+
+def main() -> int:
+    ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dst = os.path.join(root, "baseline", "_ref_tests")
+    os.makedirs(dst, exist_ok=True)
+    for f in FILES:
+        shutil.copyfile(os.path.join(ref, "tests", "shogi", f), os.path.join(dst, f))
+    print(f"copied {len(FILES)} files to {dst}")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
