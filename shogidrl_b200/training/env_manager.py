@@ -106,12 +106,16 @@ class EnvManager:
             if self.action_space_size <= 0:
                 self.logger_func("Environment validation failed: invalid action space size")
                 return False
-            obs = self.game.reset()
-            if obs is None or tuple(obs.shape) != tuple(self.obs_space_shape or ()):
-                self.logger_func("Environment validation failed: observation shape mismatch")
+            first = self.game.get_observation()
+            if not self.reset_game():
+                self.logger_func("Environment validation failed: game reset failed")
                 return False
-            if not hasattr(self.game, "get_legal_moves") or not self.game.get_legal_moves():
-                self.logger_func("Environment validation failed: no legal moves from the start position")
+            if not np.array_equal(first, self.game.get_observation()):
+                self.logger_func("Environment validation warning: Observation after reset differs from initial "
+                                 "observation. This might be expected if seeding is not deterministic or initial "
+                                 "state has randomness.")
+            if self.obs_space_shape is None or len(self.obs_space_shape) != 3:
+                self.logger_func("Environment validation failed: invalid observation space shape")
                 return False
             self.logger_func("Environment validation passed")
             return True
@@ -128,12 +132,19 @@ class EnvManager:
 
     def setup_seeding(self, seed: Optional[int] = None):
         seed_value = seed if seed is not None else getattr(self.config.env, "seed", None)
-        if seed_value is None or self.game is None:
+        if not self.game:
+            self.logger_func("Error: Game not initialized. Cannot set seed.")
+            return False
+        if seed_value is None:
+            self.logger_func("No seed value provided for re-seeding.")
+            return False
+        if not hasattr(self.game, "seed"):
+            self.logger_func(f"Warning: Game object does not have a 'seed' method. Cannot re-seed with {seed_value}.")
             return False
         try:
             self.game.seed(seed_value)
             self.logger_func(f"Environment re-seeded with: {seed_value}")
             return True
         except Exception as e:
-            self.logger_func(f"Error setting up seeding: {e}")
+            self.logger_func(f"Error setting environment seed: {e}")
             return False

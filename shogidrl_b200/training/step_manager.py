@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from ..shogi.definitions import Color
+from ..utils.move_formatting import format_move_with_description_enhanced
 
 _CAPTURE_VALUE = {"PAWN": 1, "LANCE": 3, "KNIGHT": 3, "SILVER": 5, "GOLD": 6, "BISHOP": 8, "ROOK": 10}
 
@@ -141,15 +142,30 @@ class StepManager:
             else:
                 self.gote_promo_count += 1
 
-    def _handle_demo_mode(self, move, episode_length: int, piece) -> None:
-        name = getattr(getattr(piece, "type", None), "name", "piece")
+    def _prepare_demo_info(self, legal_shogi_moves) -> Optional[Any]:
+        """The piece the FIRST legal move would move (None for drops / bad input): step_manager.py:536-560."""
+        if not legal_shogi_moves or legal_shogi_moves[0] is None:
+            return None
         try:
-            usi = self.policy_mapper.shogi_move_to_usi(move)
-        except Exception:
-            usi = str(move)
-        self.move_log.append(f"Move {episode_length + 1}: {usi} ({name})")
-        delay = getattr(self.config.display, "turn_tick", 0.0)
-        if delay and delay > 0:
+            mv = legal_shogi_moves[0]
+            if len(mv) == 5 and mv[0] is not None and mv[1] is not None:
+                return self.game.get_piece(mv[0], mv[1])
+        except (AttributeError, IndexError, ValueError):
+            pass
+        return None
+
+    def _handle_demo_mode(self, selected_move: Tuple, episode_length: int, piece_info_for_demo: Optional[Any]) -> None:
+        """Move-log line "Move N (Sente|Gote): <usi> - <description>." + the optional per-move delay (:562-608)."""
+        if hasattr(self.game, "current_player"):
+            player = getattr(self.game.current_player, "name", str(self.game.current_player))
+        else:
+            player = "Unknown"
+        text = format_move_with_description_enhanced(selected_move, self.policy_mapper, piece_info_for_demo)
+        shown = {"BLACK": "Sente", "WHITE": "Gote"}.get(player.upper(), player)
+        self.move_log.append(f"Move {episode_length + 1} ({shown}): {text}")
+        self.move_history.append(selected_move)
+        delay = self.config.display.turn_tick
+        if delay > 0:
             time.sleep(delay)
 
     def handle_episode_end(self, episode_state: EpisodeState, step_result: StepResult, game_stats: Dict[str, int],
@@ -157,8 +173,9 @@ class StepManager:
                            ) -> Tuple[EpisodeState, Optional[str]]:
         winner, reason = self._determine_winner_and_reason(step_result.info)
         stats = dict(game_stats)
-        key = {"black": "black_wins", "white": "white_wins", None: "draws"}[winner]
-        stats[key] = stats.get(key, 0) + 1
+        key = {"black": "black_wins", "white": "white_wins", None: "draws"}.get(winner)
+        if key is not None:
+            stats[key] = stats.get(key, 0) + 1
         total = stats["black_wins"] + stats["white_wins"] + stats["draws"]
         rate = (lambda k: stats[k] / total if total > 0 else 0.0)
         logger_func(
@@ -183,19 +200,30 @@ class StepManager:
             logger_func(f"CRITICAL: Game reset failed after episode end: {e}", True, None, "error")
             return episode_state, winner
 
-    @staticmethod
-    def _determine_winner_and_reason(info: Dict[str, Any]) -> Tuple[Optional[str], str]:
-        w = info.get("winner")
-        winner = w.lower() if isinstance(w, str) and w.lower() in ("black", "white") else None
-        return winner, info.get("reason", "Unknown")
+    def _determine_winner_and_reason(self, step_info: Optional[Dict[str, Any]]) -> Tuple[Optional[str], str]:
+        """(winner in lower case | None, reason) from the step's info; a "Tsumi" without a winner entry takes the game's
+        own winner (step_manager.py:610-634)."""
+        winner, reason = None, "Unknown"
+        if step_info:
+            winner = step_info.get("winner")
+            reason = step_info.get("reason", "Unknown")
+        final = winner.lower() if winner and isinstance(winner, str) else winner
+        if reason == "Tsumi" and winner is None and getattr(self.game, "winner", None) is not None:
+            if self.game.winner == Color.BLACK:
+                final = "black"
+            elif self.game.winner == Color.WHITE:
+                final = "white"
+        return final, reason
 
     @staticmethod
     def _format_game_outcome_message(winner: Optional[str], reason: str) -> str:
         if winner == "black":
-            return f"Sente (Black) wins by {reason}."
+            return f"Sente wins by {reason}."
         if winner == "white":
-            return f"Gote (White) wins by {reason}."
-        return f"Draw by {reason}."
+            return f"Gote wins by {reason}."
+        if winner is None:
+            return f"Draw by {reason}."
+        return f"Game ended: {winner} by {reason}."
 
     def reset_episode(self) -> EpisodeState:
         obs = self.game.reset()

@@ -4,6 +4,10 @@ classes through the keisei -> shogidrl_b200 alias package (tests/ref_alias).  Ru
 
     python tests/fetch_reference_tests.py [/root/reference]
 
+The mock-driven tests of the two training-side callers of the path (tests/training/test_step_manager.py and
+test_env_manager.py, with the reference's conftest.py for their fixtures) go to baseline/_ref_tests/host/; they need no
+GPU and run in the CPU suite too (tests/test_reference_host_suite_cpu.py).
+
 The copies are never committed (the reference's sources do not belong in this repository)."""
 import os
 import shutil
@@ -12,6 +16,7 @@ import sys
 FILES = ["test_legal_mask_generation.py", "test_shogi_rules_and_validation.py", "test_shogi_game_core_logic.py",
          "test_shogi_engine_integration.py", "test_shogi_game_rewards.py", "test_shogi_utils.py",
          "test_observation_constants.py", "test_reward_with_flipped_perspective.py"]
+HOST_FILES = [("", "conftest.py"), ("training", "test_step_manager.py"), ("training", "test_env_manager.py")]
 
 
 def main() -> int:
@@ -21,7 +26,11 @@ def main() -> int:
     os.makedirs(dst, exist_ok=True)
     for f in FILES:
         shutil.copyfile(os.path.join(ref, "tests", "shogi", f), os.path.join(dst, f))
-    print(f"copied {len(FILES)} files to {dst}")
+    host = os.path.join(dst, "host")
+    os.makedirs(host, exist_ok=True)
+    for sub, f in HOST_FILES:
+        shutil.copyfile(os.path.join(ref, "tests", sub, f), os.path.join(host, f))
+    print(f"copied {len(FILES)} + {len(HOST_FILES)} files to {dst}")
     return 0
 
 

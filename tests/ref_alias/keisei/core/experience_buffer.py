@@ -1,5 +1,5 @@
 import sys
 
-import shogidrl_b200.shogi.shogi_game as _m
+import shogidrl_b200.core.experience_buffer as _m
 
 sys.modules[__name__] = _m  # the very module: unittest.mock.patch on this name patches the class under test

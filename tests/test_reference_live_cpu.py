@@ -195,3 +195,32 @@ def test_oracle_rule_queries_match_the_reference(ref):
                 for t in range(7):
                     assert o.can_drop(t, sq, color.value) == bool(g.can_drop_piece(PieceType(t), sq // 9, sq % 9, color)), (t, sq)
     assert ufz >= 1  # the known-answer uchifuzume position is among the cases
+
+
+def test_move_descriptions_identical(ref):
+    """shogidrl_b200.utils.move_formatting writes the reference's demo-log strings (keisei/utils/move_formatting.py):
+    every board move and drop of the 13,527-entry table, with and without the piece, promotions and odd inputs."""
+    import keisei.utils.move_formatting as rmf
+    from keisei.shogi.shogi_core_definitions import Color as RColor, Piece as RPiece, PieceType as RPT
+    from keisei.utils import PolicyOutputMapper as RefMapper
+    import shogidrl_b200.utils.move_formatting as mf
+    from shogidrl_b200.shogi.definitions import Color, Piece, PieceType
+    from shogidrl_b200.utils import PolicyOutputMapper
+
+    rmap, omap = RefMapper(), PolicyOutputMapper()
+    rng = random.Random(5)
+    for idx in rng.sample(range(13527), 1500):
+        rmove, omove = rmap.policy_index_to_shogi_move(idx), omap.policy_index_to_shogi_move(idx)
+        assert rmf.format_move_with_description(rmove, rmap) == mf.format_move_with_description(omove, omap)
+        assert rmf.format_move_with_description_enhanced(rmove, rmap, None) == \
+            mf.format_move_with_description_enhanced(omove, omap, None)
+        v = rng.randrange(14)
+        assert rmf.format_move_with_description_enhanced(rmove, rmap, RPiece(RPT(v), RColor.BLACK)) == \
+            mf.format_move_with_description_enhanced(omove, omap, Piece(PieceType(v), Color.BLACK))
+    for v in range(14):
+        for promo in (False, True):
+            assert rmf._get_piece_name(RPT(v), promo) == mf._get_piece_name(PieceType(v), promo)
+    assert rmf.format_move_with_description(None, rmap) == mf.format_move_with_description(None, omap) == "None"
+    assert rmf.format_move_with_description_enhanced(None, rmap) == mf.format_move_with_description_enhanced(None, omap)
+    assert [rmf._coords_to_square_name(r, c) for r in range(9) for c in range(9)] == \
+        [mf._coords_to_square_name(r, c) for r in range(9) for c in range(9)]

@@ -81,7 +81,7 @@ def test_counters_and_episode_end():
     assert winner == "black" and new_state.episode_length == 0 and sm.sente_drop_count == 0
     kw = log.call_args[1]
     assert kw["wandb_data"]["black_wins_total"] == 2 and abs(kw["wandb_data"]["black_win_rate"] - 2 / 3) < 1e-9
-    assert "Sente (Black) wins by Tsumi." in log.call_args[0][0]
+    assert "Sente wins by Tsumi." in log.call_args[0][0]
     st2 = sm.update_episode_state(st, res)
     assert st2.episode_length == 1 and st2.episode_reward == 0.5
 
