@@ -74,77 +74,63 @@ class EnvManager:
                 "num_actions_total": self.config.env.num_actions_total, "seed": getattr(self.config.env, "seed", None),
                 "game_type": type(self.game).__name__, "policy_mapper_type": type(self.policy_output_mapper).__name__}
 
+    def _refuse(self, message: str, result=False):
+        """Log ``message`` and hand back the failure value: every helper below reports problems this way, never by raising."""
+        self.logger_func(message)
+        return result
+
+    def _guarded(self, what: str, fn, on_error):
+        try:
+            return fn()
+        except Exception as e:
+            return self._refuse(f"{what}: {e}", on_error)
+
     def reset_game(self) -> bool:
         if not self.game:
-            self.logger_func("Error: Game not initialized. Cannot reset.")
-            return False
-        try:
-            self.game.reset()
-            return True
-        except Exception as e:
-            self.logger_func(f"Error resetting game: {e}")
-            return False
+            return self._refuse("Error: Game not initialized. Cannot reset.")
+        return self._guarded("Error resetting game", lambda: (self.game.reset(), True)[1], False)
 
     def initialize_game_state(self) -> Optional[np.ndarray]:
         if not self.game:
-            self.logger_func("Error: Game not initialized. Cannot get initial observation.")
-            return None
-        try:
-            return self.game.reset()
-        except Exception as e:
-            self.logger_func(f"Error initializing game state: {e}")
-            return None
+            return self._refuse("Error: Game not initialized. Cannot get initial observation.", None)
+        return self._guarded("Error initializing game state", self.game.reset, None)
 
     def validate_environment(self) -> bool:
-        try:
-            if self.game is None:
-                self.logger_func("Environment validation failed: game not initialized")
-                return False
-            if self.policy_output_mapper is None:
-                self.logger_func("Environment validation failed: policy mapper not initialized")
-                return False
-            if self.action_space_size <= 0:
-                self.logger_func("Environment validation failed: invalid action space size")
-                return False
-            first = self.game.get_observation()
+        """Game and mapper present, action space non-empty, reset works, observation shape is (C, 9, 9)."""
+        def checks() -> bool:
+            for missing, what in ((self.game is None, "game not initialized"),
+                                  (self.policy_output_mapper is None, "policy mapper not initialized"),
+                                  (self.action_space_size <= 0, "invalid action space size")):
+                if missing:
+                    return self._refuse(f"Environment validation failed: {what}")
+            before = self.game.get_observation()
             if not self.reset_game():
-                self.logger_func("Environment validation failed: game reset failed")
-                return False
-            if not np.array_equal(first, self.game.get_observation()):
+                return self._refuse("Environment validation failed: game reset failed")
+            if not np.array_equal(before, self.game.get_observation()):
                 self.logger_func("Environment validation warning: Observation after reset differs from initial "
                                  "observation. This might be expected if seeding is not deterministic or initial "
                                  "state has randomness.")
             if self.obs_space_shape is None or len(self.obs_space_shape) != 3:
-                self.logger_func("Environment validation failed: invalid observation space shape")
-                return False
+                return self._refuse("Environment validation failed: invalid observation space shape")
             self.logger_func("Environment validation passed")
             return True
-        except Exception as e:
-            self.logger_func(f"Environment validation failed with exception: {e}")
-            return False
+        return self._guarded("Environment validation failed with exception", checks, False)
 
     def get_legal_moves_count(self) -> int:
-        try:
-            return len(self.game.get_legal_moves()) if self.game else 0
-        except Exception as e:
-            self.logger_func(f"Error getting legal moves count: {e}")
-            return 0
+        return self._guarded("Error getting legal moves count",
+                             lambda: len(self.game.get_legal_moves()) if self.game else 0, 0)
 
     def setup_seeding(self, seed: Optional[int] = None):
-        seed_value = seed if seed is not None else getattr(self.config.env, "seed", None)
+        seed_value = getattr(self.config.env, "seed", None) if seed is None else seed
         if not self.game:
-            self.logger_func("Error: Game not initialized. Cannot set seed.")
-            return False
+            return self._refuse("Error: Game not initialized. Cannot set seed.")
         if seed_value is None:
-            self.logger_func("No seed value provided for re-seeding.")
-            return False
+            return self._refuse("No seed value provided for re-seeding.")
         if not hasattr(self.game, "seed"):
-            self.logger_func(f"Warning: Game object does not have a 'seed' method. Cannot re-seed with {seed_value}.")
-            return False
-        try:
+            return self._refuse(f"Warning: Game object does not have a 'seed' method. Cannot re-seed with {seed_value}.")
+
+        def reseed() -> bool:
             self.game.seed(seed_value)
             self.logger_func(f"Environment re-seeded with: {seed_value}")
             return True
-        except Exception as e:
-            self.logger_func(f"Error setting environment seed: {e}")
-            return False
+        return self._guarded("Error setting environment seed", reseed, False)
