@@ -215,6 +215,42 @@ __global__ void __launch_bounds__(128) fill_np(uint4* p, size_t n16) {  // non-p
   for (int k = 0; k < 4; k++) { const size_t i = i0 + k * stride; if (i < n16) p[i] = make_uint4(0, 0, 0, 0); }
 }
 
+
+// ---- round-2 follow-up: is it the persistent grid or the access pattern that costs the 15 % between 0.30 and 0.255 ms?
+// np_flat256: one CTA per 8 KB, 256-bit stores (the persistent flat fill's pattern, non-persistent)
+__global__ void __launch_bounds__(256) np_flat256(uint8_t* base, size_t total_kb) {
+  const size_t i = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i < total_kb) st_zero256(base + i * 1024 + (threadIdx.x & 31) * 32);
+}
+// np_rows: one CTA per tile of 8 games, one warp per game: its mask row, then its observation row (kz_step's layout), zeros
+__global__ void __launch_bounds__(256) np_rows(uint8_t* mask, float* obs, int n) {
+  const int lane = threadIdx.x & 31, g = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (g >= n) return;
+  uint8_t* mrow = mask + (size_t)g * MASK_STRIDE;
+  for (int q = lane; q < MASK_STRIDE / 32; q += 32) st_zero256(mrow + 32 * q);
+  char* orow = reinterpret_cast<char*>(obs) + (size_t)g * OBS_FLOATS * 4;
+  const int head = (int)(((32u - (unsigned)((uintptr_t)orow & 31)) & 31u) >> 3);
+  const int nb = (OBS_FLOATS * 4 - head * 8) >> 5;
+  if (lane < head) reinterpret_cast<float2*>(orow)[lane] = make_float2(0.f, 0.f);
+  for (int q = lane; q < nb; q += 32) st_zero256(orow + head * 8 + 32 * q);
+  const int tail0 = head + 4 * nb;
+  if (lane < OBS_FLOATS / 2 - tail0) reinterpret_cast<float2*>(orow)[tail0 + lane] = make_float2(0.f, 0.f);
+}
+// p_streams: persistent grid, every thread keeps 4 far-apart streams of 16-byte stores (fill_np's pattern, persistent)
+__global__ void __launch_bounds__(128) p_streams(uint4* p, size_t n16) {
+  const size_t q = n16 / 4;
+  for (size_t i = (size_t)blockIdx.x * 128 + threadIdx.x; i < q; i += (size_t)gridDim.x * 128) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) p[i + k * q] = make_uint4(0, 0, 0, 0);
+  }
+}
+// np_contig: non-persistent, 64 contiguous bytes per thread as 4 x 16 B, CTA of 128 threads covers 8 KB
+__global__ void __launch_bounds__(128) np_contig(uint4* p, size_t n16) {
+  const size_t i0 = (size_t)blockIdx.x * 512 + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { const size_t i = i0 + k * 128; if (i < n16) p[i] = make_uint4(0, 0, 0, 0); }
+}
+
 int main() {
   const int n = 65536;
   uint8_t* buf;
@@ -272,6 +308,28 @@ int main() {
     ms /= 10;
     printf("%-44s%9.4f   %.0f GB/s  (non-persistent grid of %u CTAs x 128 threads x 64 B)\n", "flat fill, elementwise-style", ms,
            (double)(mask_bytes + obs_bytes) / ms / 1e6, grid);
+  }
+  {  // round-2 follow-up: non-persistent / multi-stream variants of the same bytes
+    const size_t total = mask_bytes + obs_bytes, n16 = total / 16;
+    auto timeit = [&](const char* name, auto launch) {
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0); cudaEventCreate(&e1);
+      for (int i = 0; i < 3; i++) launch();
+      cudaEventRecord(e0);
+      for (int i = 0; i < 10; i++) launch();
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float ms;
+      cudaEventElapsedTime(&ms, e0, e1);
+      ms /= 10;
+      printf("%-60s%9.4f   %.0f GB/s  (%s)\n", name, ms, (double)total / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
+    };
+    timeit("non-persistent, CTA = 8 KB flat, 256-bit stores", [&] { np_flat256<<<(unsigned)((total / 1024 + 7) / 8), 256>>>(buf, total / 1024); });
+    timeit("non-persistent, CTA = tile of 8 games, warp = one game's rows", [&] { np_rows<<<n / 8, 256>>>(mask, obs, n); });
+    timeit("non-persistent, 64 contiguous bytes per thread", [&] { np_contig<<<(unsigned)((n16 + 511) / 512), 128>>>(reinterpret_cast<uint4*>(buf), n16); });
+    for (int c : {4, 8, 16})
+      timeit(c == 4 ? "persistent x4 CTAs(128)/SM, 4 far streams per thread" : c == 8 ? "persistent x8" : "persistent x16",
+             [&] { p_streams<<<sms * c, 128>>>(reinterpret_cast<uint4*>(buf), n16); });
   }
   return 0;
 }
