@@ -251,6 +251,54 @@ __global__ void __launch_bounds__(128) np_contig(uint4* p, size_t n16) {
   for (int k = 0; k < 4; k++) { const size_t i = i0 + k * 128; if (i < n16) p[i] = make_uint4(0, 0, 0, 0); }
 }
 
+// ---- second follow-up: which property of the fast non-persistent fills matters?
+// p_chunk: persistent, CTA b owns one contiguous chunk and walks it 8 KB per iteration (page-local, unlike the grid stride)
+__global__ void __launch_bounds__(256) p_chunk(uint8_t* base, size_t total_kb) {
+  const size_t per = (total_kb / 8 + gridDim.x - 1) / gridDim.x;  // 8 KB pieces per CTA
+  const size_t lo = (size_t)blockIdx.x * per, hi = lo + per < total_kb / 8 ? lo + per : total_kb / 8;
+  for (size_t i = lo; i < hi; i++) st_zero256(base + (i * 8 + (threadIdx.x >> 5)) * 1024 + (threadIdx.x & 31) * 32);
+}
+// np_run: non-persistent, CTA writes R consecutive 8 KB pieces
+__global__ void __launch_bounds__(256) np_run(uint8_t* base, size_t total_kb, int R) {
+  for (int r = 0; r < R; r++) {
+    const size_t i = ((size_t)blockIdx.x * R + r) * 8 + (threadIdx.x >> 5);
+    if (i < total_kb) st_zero256(base + i * 1024 + (threadIdx.x & 31) * 32);
+  }
+}
+// np_tile_flat: non-persistent, CTA = tile of 8 games, but the CTA's 8 warps write the tile's 8 mask rows as ONE flat block
+// (consecutive warps -> consecutive KB), then the 8 observation rows the same way
+__global__ void __launch_bounds__(256) np_tile_flat(uint8_t* mask, float* obs, int n) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* mb = mask + (size_t)blockIdx.x * 8 * MASK_STRIDE;        // 108,288 B, 32-byte aligned
+  for (int q = w; q < 8 * MASK_STRIDE / 1024; q += 8) st_zero256(mb + q * 1024 + lane * 32);
+  if (w == 0 && lane < (8 * MASK_STRIDE % 1024) / 32) st_zero256(mb + (8 * MASK_STRIDE / 1024) * 1024 + lane * 32);
+  uint8_t* ob = reinterpret_cast<uint8_t*>(obs) + (size_t)blockIdx.x * 8 * OBS_FLOATS * 4;  // 119,232 B, 32-byte aligned
+  for (int q = w; q < 8 * OBS_FLOATS * 4 / 1024; q += 8) st_zero256(ob + q * 1024 + lane * 32);
+  if (w == 0 && lane < (8 * OBS_FLOATS * 4 % 1024) / 32) st_zero256(ob + (8 * OBS_FLOATS * 4 / 1024) * 1024 + lane * 32);
+}
+// p_rows_dyn: persistent per-warp rows (zeros) with dynamically claimed tiles (no static-stride tail)
+__global__ void __launch_bounds__(256) p_rows_dyn(uint8_t* mask, float* obs, int n, int* counter) {
+  __shared__ int s_t;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int tile = blockIdx.x;
+  while (tile < n / 8) {
+    const int g = tile * 8 + w;
+    uint8_t* mrow = mask + (size_t)g * MASK_STRIDE;
+    for (int q = lane; q < MASK_STRIDE / 32; q += 32) st_zero256(mrow + 32 * q);
+    char* orow = reinterpret_cast<char*>(obs) + (size_t)g * OBS_FLOATS * 4;
+    const int head = (int)(((32u - (unsigned)((uintptr_t)orow & 31)) & 31u) >> 3);
+    const int nb = (OBS_FLOATS * 4 - head * 8) >> 5;
+    if (lane < head) reinterpret_cast<float2*>(orow)[lane] = make_float2(0.f, 0.f);
+    for (int q = lane; q < nb; q += 32) st_zero256(orow + head * 8 + 32 * q);
+    const int tail0 = head + 4 * nb;
+    if (lane < OBS_FLOATS / 2 - tail0) reinterpret_cast<float2*>(orow)[tail0 + lane] = make_float2(0.f, 0.f);
+    __syncthreads();
+    if (threadIdx.x == 0) s_t = gridDim.x + atomicAdd(counter, 1);
+    __syncthreads();
+    tile = s_t;
+  }
+}
+
 int main() {
   const int n = 65536;
   uint8_t* buf;
@@ -330,6 +378,37 @@ int main() {
     for (int c : {4, 8, 16})
       timeit(c == 4 ? "persistent x4 CTAs(128)/SM, 4 far streams per thread" : c == 8 ? "persistent x8" : "persistent x16",
              [&] { p_streams<<<sms * c, 128>>>(reinterpret_cast<uint4*>(buf), n16); });
+  }
+  {  // second follow-up
+    const size_t total = mask_bytes + obs_bytes;
+    int* counter;
+    cudaMalloc(&counter, 4);
+    auto timeit = [&](const char* name, auto launch) {
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0); cudaEventCreate(&e1);
+      for (int i = 0; i < 3; i++) launch();
+      cudaEventRecord(e0);
+      for (int i = 0; i < 10; i++) launch();
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float ms;
+      cudaEventElapsedTime(&ms, e0, e1);
+      ms /= 10;
+      printf("%-72s%9.4f   %.0f GB/s  (%s)\n", name, ms, (double)total / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
+    };
+    char nm[128];
+    for (int c : {1, 3, 8}) { snprintf(nm, sizeof nm, "persistent flat, CTA-contiguous chunks, %d CTAs/SM", c); timeit(nm, [&] { p_chunk<<<sms * c, 256>>>(buf, total / 1024); }); }
+    for (int R : {4, 16, 64, 256}) { snprintf(nm, sizeof nm, "non-persistent flat, %d x 8 KB per CTA", R); timeit(nm, [&] { np_run<<<(unsigned)((total / 8192 + R - 1) / R), 256>>>(buf, total / 1024, R); }); }
+    timeit("non-persistent, CTA = tile, rows written as flat blocks by the CTA", [&] { np_tile_flat<<<n / 8, 256>>>(mask, obs, n); });
+    for (int kb : {0, 24, 48, 72, 100, 200}) {  // dynamic shared memory caps the resident CTAs per SM: 8, 8, 4, 3, 2, 1
+      cudaFuncSetAttribute(np_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      snprintf(nm, sizeof nm, "non-persistent per-warp rows, %d KB dynamic smem per CTA (caps residency)", kb);
+      timeit(nm, [&] { np_rows<<<n / 8, 256, kb * 1024>>>(mask, obs, n); });
+    }
+    for (int c : {1, 2, 3, 4}) {
+      snprintf(nm, sizeof nm, "persistent per-warp rows, dynamic tile claims, %d CTAs/SM", c);
+      timeit(nm, [&] { cudaMemsetAsync(counter, 0, 4); p_rows_dyn<<<sms * c, 256>>>(mask, obs, n, counter); });
+    }
   }
   return 0;
 }
