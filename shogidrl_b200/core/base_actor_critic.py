@@ -12,6 +12,7 @@ its checkpoints load."""
 from __future__ import annotations
 
 import itertools
+import sys
 from typing import Optional, Tuple
 
 import torch
@@ -78,6 +79,12 @@ class BaseActorCriticModel(nn.Module):
     def evaluate_actions(self, obs: torch.Tensor, actions: torch.Tensor, legal_mask: Optional[torch.Tensor] = None
                          ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         logits, value = self.forward(obs)
+        if legal_mask is not None and not rl.is_bitmap(legal_mask) and legal_mask.dim() == 2 \
+                and not bool(legal_mask.bool().any(dim=1).all()):
+            # the public method reports rows without a legal action as the reference does (base_actor_critic.py:166-174);
+            # the PPO update goes through evaluate_from_logits and never synchronises
+            print(f"[{self.__class__.__name__}] ERROR: NaNs in probabilities in evaluate_actions. Check legal_mask and "
+                  "logits. Defaulting to uniform for affected rows.", file=sys.stderr)
         return self.evaluate_from_logits(logits, value, actions, legal_mask)
 
     @staticmethod

@@ -136,6 +136,10 @@ class PPOAgent:
         obs_tensor = torch.as_tensor(obs, dtype=torch.float32, device=self.device).unsqueeze(0)
         if not bool(legal_mask.any()):
             _log("ERROR", "select_action called with no legal moves (based on input legal_mask)")
+            # ... and the line the reference's model prints when every logit is masked (base_actor_critic.py:92-101); the
+            # sampling kernel falls back to the same uniform distribution without a host round trip, so it is said here
+            print(f"[{type(getattr(self.model, 'module', self.model)).__name__}] ERROR: NaNs in probabilities in "
+                  "get_action_and_value. Check legal_mask and logits. Defaulting to uniform.", file=sys.stderr)
         action, log_prob, value = self.select_actions(obs_tensor, legal_mask.to(self.device), is_training=is_training)
         idx, lp, v = int(action.item()), float(log_prob.item()), float(value.item())
         try:

@@ -701,3 +701,34 @@ def test_rule_queries_match_oracle_on_random_endgames():
                     assert game.can_drop_piece(PieceType(t), sq // 9, sq % 9, color) == want, (i, color, t, sq)
                     drops += int(want)
     assert drops > 500
+
+
+def test_no_legal_action_rows_fall_back_to_uniform_and_say_so(capsys):
+    """A legal mask without any legal action: the reference masks every logit to -inf, gets NaN probabilities, reports
+    them on stderr and continues with a uniform distribution (base_actor_critic.py:92-101, 166-174; ppo_agent.py:160-168).
+    The kernels take the same fallback; the facade prints the same lines."""
+    import math
+    from shogidrl_b200.core import ActorCritic, PPOAgent
+    cfg = make_config()
+    torch.manual_seed(3)
+    agent = PPOAgent(ActorCritic(46, 13527), cfg, torch.device("cuda"))
+    obs = np.zeros((46, 9, 9), np.float32)
+    none_legal = torch.zeros(13527, dtype=torch.bool, device="cuda")
+    move, idx, lp, v = agent.select_action(obs, none_legal, is_training=True)
+    err = capsys.readouterr().err
+    assert "[PPOAgent] ERROR: select_action called with no legal moves (based on input legal_mask)" in err
+    assert "[ActorCritic] ERROR: NaNs in probabilities in get_action_and_value. Check legal_mask and logits. Defaulting to uniform." in err
+    assert 0 <= idx < 13527 and abs(lp - math.log(1.0 / 13527)) < 1e-4 and np.isfinite(v) and move is not None
+    masks = torch.zeros((3, 13527), dtype=torch.bool, device="cuda")
+    masks[1, 100:140] = True
+    acts = torch.tensor([5, 120, 13000], device="cuda")
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logp, ent, val = agent.model.evaluate_actions(torch.zeros((3, 46, 9, 9), device="cuda"), acts, masks)
+    err = capsys.readouterr().err
+    assert "[ActorCritic] ERROR: NaNs in probabilities in evaluate_actions. Check legal_mask and logits. Defaulting to uniform for affected rows." in err
+    assert torch.isfinite(logp).all() and torch.isfinite(ent).all() and torch.isfinite(val).all()
+    for r in (0, 2):
+        assert abs(float(logp[r]) - math.log(1.0 / 13527)) < 1e-4 and abs(float(ent[r]) - math.log(13527)) < 1e-3
+    assert float(ent[1]) <= math.log(40) + 1e-4
+    agent.model.evaluate_actions(torch.zeros((1, 46, 9, 9), device="cuda"), acts[1:2], masks[1:2])
+    assert "NaNs" not in capsys.readouterr().err
