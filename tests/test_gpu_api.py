@@ -723,7 +723,7 @@ def test_no_legal_action_rows_fall_back_to_uniform_and_say_so(capsys):
     masks[1, 100:140] = True
     acts = torch.tensor([5, 120, 13000], device="cuda")
     with torch.autocast("cuda", dtype=torch.bfloat16):
-        logp, ent, val = agent.model.evaluate_actions(torch.zeros((3, 46, 9, 9), device="cuda"), acts, masks)
+        logp, ent, val = (t.detach() for t in agent.model.evaluate_actions(torch.zeros((3, 46, 9, 9), device="cuda"), acts, masks))
     err = capsys.readouterr().err
     assert "[ActorCritic] ERROR: NaNs in probabilities in evaluate_actions. Check legal_mask and logits. Defaulting to uniform for affected rows." in err
     assert torch.isfinite(logp).all() and torch.isfinite(ent).all() and torch.isfinite(val).all()

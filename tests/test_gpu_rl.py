@@ -552,7 +552,7 @@ def test_input_layer_from_compact_observations(relu):
     ref = torch.nn.functional.conv2d(obs[rows].bfloat16().float(), w.detach().bfloat16().float(), b.detach().bfloat16().float(), padding=1)
     ref = torch.relu(ref) if relu else ref
     scale = float(ref.abs().max())
-    assert float((y_c.float() - ref).abs().max()) <= 2.0 ** -7 * scale + 1e-3   # bf16 output rounding
+    assert float((y_c.detach().float() - ref).abs().max()) <= 2.0 ** -7 * scale + 1e-3   # bf16 output rounding
     assert float((y_c.float() - y_d.float()).abs().max()) <= 2.0 ** -7 * scale + 1e-3
     assert float((y_c.float() - y_d.float()).abs().mean()) <= 1e-4 * scale           # almost always the same bf16 value
     dy = torch.randn(y_c.shape, generator=torch.Generator(device="cpu").manual_seed(5)).to(dev).bfloat16()
