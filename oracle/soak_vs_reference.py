@@ -3,7 +3,7 @@ on fresh random games -- from the start position and from drop-heavy endgames lo
 Compared at every ply: the legal action set, and after the move reward / done / winner / reason, the 46-plane observation
 and the position (SFEN of the reference vs the oracle's export).  Needs the reference checkout:
 
-    python oracle/soak_vs_reference.py --minutes 20 --procs 8 [--ref /root/reference] [--seed 1]
+    python oracle/soak_vs_reference.py --minutes 20 --procs 8 [--ref /root/reference] [--seed 1] [--sparse]
 
 Prints one summary line per process and exits non-zero on the first divergence (with the seed that reproduces it)."""
 import argparse
@@ -17,8 +17,33 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REASONS = {"Tsumi": 1, "stalemate": 2, "Max moves reached": 3, "Sennichite": 4}  # KZ_* codes of include/keisei_b200.h
 
 
+def _sparse_positions(n, seed):
+    """Kings and at most three non-pawn pieces, empty hands: random play from these repeats positions (sennichite)."""
+    import numpy as np
+    from oracle import oracle as orc
+    rng = np.random.default_rng(seed)
+    boards, hands, sides = [], [], []
+    while len(boards) < n:
+        b = np.zeros(81, np.int8)
+        k0, k1 = rng.choice(81, 2, replace=False)
+        if max(abs(k0 // 9 - k1 // 9), abs(k0 % 9 - k1 % 9)) < 2:
+            continue
+        b[k0], b[k1] = 8, 22
+        for _ in range(int(rng.integers(0, 4))):
+            sq, t, color = int(rng.integers(0, 81)), int(rng.choice([3, 4, 5, 6, 12, 13])), int(rng.integers(0, 2))
+            if b[sq] == 0:
+                b[sq] = 1 + t + 14 * color
+        side = int(rng.integers(0, 2))
+        h = np.zeros(14, np.uint8)
+        g = orc.OracleGame.from_arrays(b, h, side, 0, 500, evaluate_termination=False)
+        if g.in_check(1 - side) or len(g.legal_indices()) == 0:
+            continue
+        boards.append(b); hands.append(h); sides.append(side)
+    return np.stack(boards), np.stack(hands), np.asarray(sides, np.uint8)
+
+
 def _worker(args):
-    ref_dir, seed, deadline, max_moves = args
+    ref_dir, seed, deadline, max_moves, sparse = args
     sys.dont_write_bytecode = True
     sys.path.insert(0, ROOT)
     sys.path.append(ref_dir)
@@ -32,13 +57,13 @@ def _worker(args):
     rng = random.Random(seed)
     plies = games = 0
     ends = {}
-    endgames = random_endgames(64, seed)
+    endgames = _sparse_positions(64, seed) if sparse else random_endgames(64, seed)
     gi = 0
     while time.time() < deadline:
         game_seed = rng.randrange(1 << 30)
         grng = random.Random(game_seed)
         mm = grng.choice([max_moves, 40, 120])
-        if gi % 2 == 1:
+        if sparse or gi % 2 == 1:
             k = (gi // 2) % 64
             sfen = HostPosition(endgames[0][k], endgames[1][k], int(endgames[2][k]), 0).to_sfen_string()
             g = rshogi.ShogiGame.from_sfen(sfen, mm)
@@ -86,10 +111,11 @@ def main() -> int:
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--seed", type=int, default=int.from_bytes(os.urandom(3), "little"))
     ap.add_argument("--max-moves", type=int, default=500)
+    ap.add_argument("--sparse", action="store_true", help="start every game from a few-piece position without hands (repetitions)")
     a = ap.parse_args()
     deadline = time.time() + 60 * a.minutes
     with mp.get_context("spawn").Pool(a.procs) as pool:
-        results = pool.map(_worker, [(a.ref, a.seed + i, deadline, a.max_moves) for i in range(a.procs)])
+        results = pool.map(_worker, [(a.ref, a.seed + i, deadline, a.max_moves, a.sparse) for i in range(a.procs)])
     bad = [r for r in results if r[0] != "OK"]
     for r in results:
         print(r)
