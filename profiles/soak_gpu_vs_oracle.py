@@ -55,6 +55,6 @@ ok["boards"] = np.array_equal(b, ref["boards"]) and np.array_equal(h, ref["hands
 ok["mask"] = np.array_equal(env.mask.cpu().numpy(), ref["mask"])
 ok["obs"] = np.array_equal(env.obs.cpu().numpy(), ref["obs"])
 hist = {int(k): int(v) for k, v in zip(*np.unique(ref["reasons"][ref["dones"] > 0], return_counts=True))}
-print(("drop-heavy endgame starts, " if start is not None else "") + f"{n} games x {T} steps = {n * T} env steps, max_moves {max_moves}, seed {seed}: device loop {t1 - t0:.1f} s, oracle "
+print((f"start positions from {os.environ['KZ_SOAK_START']}, " if start is not None else "") + f"{n} games x {T} steps = {n * T} env steps, max_moves {max_moves}, seed {seed}: device loop {t1 - t0:.1f} s, oracle "
       f"{t2 - t1:.1f} s on {os.cpu_count()} threads; finished episodes by reason {hist}; equal: {ok}")
 sys.exit(0 if all(ok.values()) else 1)
