@@ -11,7 +11,6 @@ history can be edited by ``undo_move``.
 """
 from __future__ import annotations
 
-import copy
 from typing import Any, Dict, List, Optional, Tuple, Union
 
 import numpy as np
