@@ -5,7 +5,8 @@ classes through the keisei -> shogidrl_b200 alias package (tests/ref_alias).  Ru
     python tests/fetch_reference_tests.py [/root/reference]
 
 The mock-driven tests of the two training-side callers of the path (tests/training/test_step_manager.py and
-test_env_manager.py, with the reference's conftest.py for their fixtures) go to baseline/_ref_tests/host/; they need no
+test_env_manager.py, with the reference's conftest.py for their fixtures) and two CPU-only files of tests/shogi
+(test_move_formatting.py, test_shogi_core_definitions.py) go to baseline/_ref_tests/host/; they need no
 GPU and run in the CPU suite too (tests/test_reference_host_suite_cpu.py).
 
 The copies are never committed (the reference's sources do not belong in this repository)."""
@@ -16,7 +17,8 @@ import sys
 FILES = ["test_legal_mask_generation.py", "test_shogi_rules_and_validation.py", "test_shogi_game_core_logic.py",
          "test_shogi_engine_integration.py", "test_shogi_game_rewards.py", "test_shogi_utils.py",
          "test_observation_constants.py", "test_reward_with_flipped_perspective.py"]
-HOST_FILES = [("", "conftest.py"), ("training", "test_step_manager.py"), ("training", "test_env_manager.py")]
+HOST_FILES = [("", "conftest.py"), ("training", "test_step_manager.py"), ("training", "test_env_manager.py"),
+              ("shogi", "test_move_formatting.py"), ("shogi", "test_shogi_core_definitions.py")]
 
 
 def main() -> int:

@@ -9,3 +9,5 @@ if os.path.isdir(_REF):
 
 from shogidrl_b200.utils import *  # noqa: F401,F403,E402
 from shogidrl_b200.utils import PolicyOutputMapper  # noqa: F401,E402  (the hot-path class: this repository's)
+from shogidrl_b200.utils.move_formatting import (_coords_to_square_name, _get_piece_name,  # noqa: F401,E402  (this repository's)
+                                                 format_move_with_description, format_move_with_description_enhanced)
