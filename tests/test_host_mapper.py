@@ -88,3 +88,18 @@ def test_definitions():
     assert p.type is PieceType.PROMOTED_PAWN and p.is_promoted and p.symbol() == "+p"
     with pytest.raises(TypeError):
         Piece(0, Color.BLACK)
+
+
+def test_sfen_square_and_drop_letter_helpers():
+    """The two private helpers of keisei/shogi/shogi_game_io.py (:744-776) that the reference's I/O tests import."""
+    from shogidrl_b200.shogi.definitions import PieceType
+    from shogidrl_b200.shogi.shogi_game_io import _get_piece_type_from_sfen_char, _parse_sfen_square, sfen_to_move_tuple
+    assert _parse_sfen_square("9a") == (0, 0) and _parse_sfen_square("1i") == (8, 8) and _parse_sfen_square("7g") == (6, 2)
+    for bad in ("", "7", "0a", "7j", "77", "7g7"):
+        with pytest.raises(ValueError, match="Invalid SFEN square format"):
+            _parse_sfen_square(bad)
+    assert [_get_piece_type_from_sfen_char(c) for c in "PLNSGBR"] == [PieceType(i) for i in range(7)]
+    for bad in ("K", "p", "+P", "X", ""):
+        with pytest.raises(ValueError, match="Invalid SFEN piece character for drop"):
+            _get_piece_type_from_sfen_char(bad)
+    assert sfen_to_move_tuple("P*5e") == (None, None, 4, 4, PieceType.PAWN) and sfen_to_move_tuple("2b3a+") == (1, 7, 0, 6, True)
