@@ -16,7 +16,11 @@ import sys
 
 FILES = ["test_legal_mask_generation.py", "test_shogi_rules_and_validation.py", "test_shogi_game_core_logic.py",
          "test_shogi_engine_integration.py", "test_shogi_game_rewards.py", "test_shogi_utils.py",
-         "test_observation_constants.py", "test_reward_with_flipped_perspective.py"]
+         "test_observation_constants.py", "test_reward_with_flipped_perspective.py",
+         "test_shogi_game_io.py", "test_shogi_game_mock_comprehensive.py"]
+# the last two import tests.utils.mock_utilities (a context manager that hides torch from NEW imports while a game is
+# built): the reference's helper module is copied next to them as a `tests` package of its own
+PKG_FILES = [("", "__init__.py"), ("utils", "__init__.py"), ("utils", "mock_utilities.py")]
 HOST_FILES = [("", "conftest.py"), ("training", "test_step_manager.py"), ("training", "test_env_manager.py"),
               ("shogi", "test_move_formatting.py"), ("shogi", "test_shogi_core_definitions.py")]
 
@@ -28,6 +32,10 @@ def main() -> int:
     os.makedirs(dst, exist_ok=True)
     for f in FILES:
         shutil.copyfile(os.path.join(ref, "tests", "shogi", f), os.path.join(dst, f))
+    for sub, f in PKG_FILES:
+        d = os.path.join(dst, "_pkg", "tests", sub)
+        os.makedirs(d, exist_ok=True)
+        shutil.copyfile(os.path.join(ref, "tests", sub, f), os.path.join(d, f))
     host = os.path.join(dst, "host")
     os.makedirs(host, exist_ok=True)
     for sub, f in HOST_FILES:
